@@ -1,0 +1,100 @@
+/* lora_b200 C-ABI: the drop-in boundary for the LoRA hot path of cloneofsimo/lora on B200 (sm_100a).
+ *
+ * Plain C: raw device pointers, sizes, dtype enums and a cudaStream_t passed as void*. No torch
+ * or ATen types cross this boundary. Every entry point enqueues work on `stream` and returns an
+ * int status immediately (0 = LB_OK, negative = refused, nothing was launched); kernels never
+ * synchronise the host. The reference has no FFI of its own (it is pure Python on top of torch
+ * eager); each entry point below names the reference code it replaces, and INTEGRATION.md shows
+ * the ctypes stub that binds it under the reference's own module classes.
+ *
+ * Conventions
+ *   - "16-bit" operands are bf16 (LB_BF16) or fp16 (LB_F16), chosen per call by in_dtype.
+ *   - LoRA master factors are fp32:   down A[r,K] row-major,   up B[N,r] row-major
+ *     (reference: lora_down.weight / lora_up.weight, lora_diffusion/lora.py:44-46).
+ *   - "down16" operands are 16-bit copies zero-padded to 16 rows: [16,K] row-major
+ *     (built by lb_cast_rows_pad16). Rank r <= 16 in this version.
+ *   - T buffers are fp32 [M,16] row-major, columns >= r are zero.
+ *   - All base pointers 16-byte aligned; K % 8 == 0; N % 8 == 0 (N % 4 for fp32 outputs).
+ */
+#ifndef LORA_B200_H
+#define LORA_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum lb_status {
+  LB_OK = 0,
+  LB_ERR_SHAPE = -1, /* unsupported / misaligned extent */
+  LB_ERR_RANK = -2,  /* r outside [1,16] */
+  LB_ERR_DTYPE = -3,
+  LB_ERR_ALIGN = -4, /* pointer not 16-byte aligned */
+  LB_ERR_TMAP = -5,  /* cuTensorMapEncodeTiled unavailable or failed */
+  LB_ERR_CUDA = -6   /* launch error (cudaGetLastError) */
+};
+
+enum lb_dtype { LB_BF16 = 0, LB_F16 = 1, LB_F32 = 2 };
+
+/* ABI version of this header (bumped on any signature change). */
+int lb_abi_version(void);
+
+/* Fused frozen linear + LoRA forward (tcgen05/TMEM/TMA), one launch:
+ *     Y[M,N] = X[M,K] . W[N,K]^T (+ bias[N]) + ((X . down16^T) * (scale * diag)) . up^T
+ * up element (n, j) is read from the fp32 master at up[n*up_rs + j*up_cs]; diag is the optional
+ * selector diagonal [r] (NULL = identity); T_out (NULL = skip) receives X . down16^T (unscaled).
+ * Replaces LoraInjectedLinear.forward, lora_diffusion/lora.py:53-58 (F.linear + lora_down +
+ * selector + lora_up + scale + add), dropout handled by the caller.
+ *
+ * The SAME entry point is the backward-dX kernel: with W := W^T[K,N] (pre-transposed frozen
+ * weight), down16 := B^T padded [16,N], up := A read transposed (up_rs = 1, up_cs = K) it returns
+ *     dX[M,K] = gY . W + ((gY . B) * (scale * diag)) . A       and  T_out = gY . B.
+ */
+int lb_lora_linear_fwd(const void* X, const void* W, const float* bias, const void* down16,
+                       const float* up, long long up_rs, long long up_cs, const float* diag,
+                       float scale, void* Y, float* T_out, int M, int K, int N, int r,
+                       int in_dtype, int out_dtype, void* stream);
+
+/* Skinny weight-gradient reduction (streams S once, fp32 atomics into out):
+ *     out[j*out_js + c*out_cs] += scale * diag[j] * sum_m V[m,j] * S[m,c]     j < r, c < C
+ * dA[r,K]: S = X[M,K],  V = gY.B (T_out of the dX call), out_js = K, out_cs = 1
+ * dB[N,r]: S = gY[M,N], V = X.A^T (T_out of the forward), out_js = 1, out_cs = r
+ * Replaces the autograd-generated dA/dB GEMMs of lora.py:53-58 (W frozen: no dW).
+ */
+int lb_lora_wgrad(const void* S, const float* V, const float* diag, float scale, float* out,
+                  long long out_js, long long out_cs, int M, int C, int r, int in_dtype,
+                  void* stream);
+
+/* dst16[j, c] = (j < r) ? src[j*src_rs + c*src_cs] : 0   for j < 16, c < C  (16-bit, [16,C]).
+ * A[r,K] -> down16:  src_rs = K, src_cs = 1.    B[N,r] -> B^T padded: src_rs = 1, src_cs = r. */
+int lb_cast_rows_pad16(const float* src, long long src_rs, long long src_cs, void* dst16, int r,
+                       int C, int out_dtype, void* stream);
+
+/* Frozen-weight preparation: src [R,C] (LB_F32/LB_BF16/LB_F16) -> dst16 [R,C] and/or
+ * dstT16 [C,R] (either may be NULL). One-time cost per frozen weight. */
+int lb_cast_weight(const void* src, int src_dtype, void* dst16, void* dstT16, int R, int C,
+                   int out_dtype, void* stream);
+
+/* Global-norm clip + AdamW over one flat fp32 arena, two launches, no host sync.
+ *   total = inv_world * ||g||_2 ; coef = min(1, max_norm / (total + 1e-6))  (max_norm <= 0: no clip)
+ *   g' = g * inv_world * coef ; decoupled weight decay ; Adam moments ; bias correction with
+ *   t = ++(*step_dev) ; g is zeroed for the next step ; *gnorm_out = total.
+ * Elements [group_off[i], group_off[i+1]) use lr_dev[i] (device array, so a captured graph sees
+ * scheduler updates). partials: scratch of >= 1024 floats.
+ * Replaces clip_grad_norm_ + torch.optim.AdamW.step + zero_grad,
+ * training_scripts/train_lora_dreambooth.py:878-888 and lora_diffusion/cli_lora_pti.py:606-609.
+ */
+int lb_adamw_clip_step(float* p, float* g, float* m, float* v, long long n,
+                       const long long* group_off, int n_groups, const float* lr_dev, float beta1,
+                       float beta2, float eps, float weight_decay, float max_norm, float inv_world,
+                       int* step_dev, float* partials, float* gnorm_out, void* stream);
+
+/* Batched 16-bit shadow refresh after an optimizer step: for every table entry e
+ *   dst16_base[e.dst_off + j*e.C + c] = (j < e.r) ? p[e.src_off + j*e.src_rs + c*e.src_cs] : 0
+ * table: device array of n_entries x 6 long long {src_off, src_rs, src_cs, r, C, dst_off}. */
+int lb_refresh_shadows(const float* p, const long long* table, int n_entries, int max_C,
+                       void* dst16_base, int out_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LORA_B200_H */

@@ -1,0 +1,83 @@
+"""ctypes binding of the C-ABI in include/lora_b200.h.
+
+The library is the product: there is no CPU or eager fallback behind these calls. Importing this
+module without a built liblora_b200.so raises, and every wrapper raises on a non-zero status.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblora_b200.so")
+
+LB_BF16, LB_F16, LB_F32 = 0, 1, 2
+
+_STATUS = {
+    0: "LB_OK", -1: "LB_ERR_SHAPE", -2: "LB_ERR_RANK", -3: "LB_ERR_DTYPE",
+    -4: "LB_ERR_ALIGN", -5: "LB_ERR_TMAP", -6: "LB_ERR_CUDA",
+}
+
+
+class LoraB200Error(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise LoraB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m lora_b200.build` "
+            "(nvcc, sm_100a). lora_b200 has no fallback path."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ll, i32, f32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float
+    sig = {
+        "lb_abi_version": ([], i32),
+        "lb_lora_linear_fwd": ([vp, vp, vp, vp, vp, ll, ll, vp, f32, vp, vp,
+                                i32, i32, i32, i32, i32, i32, vp], i32),
+        "lb_lora_wgrad": ([vp, vp, vp, f32, vp, ll, ll, i32, i32, i32, i32, vp], i32),
+        "lb_cast_rows_pad16": ([vp, ll, ll, vp, i32, i32, i32, vp], i32),
+        "lb_cast_weight": ([vp, i32, vp, vp, i32, i32, i32, vp], i32),
+        "lb_adamw_clip_step": ([vp, vp, vp, vp, ll, ctypes.POINTER(ll), i32, vp, f32, f32, f32,
+                                f32, f32, f32, vp, vp, vp, vp], i32),
+        "lb_refresh_shadows": ([vp, vp, i32, i32, vp, i32, vp], i32),
+        "lb_lora_conv2d_fwd": ([vp, vp, vp, vp, vp, ll, ll, vp, f32, vp, vp,
+                                i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
+        "lb_svd_lowrank": None,
+    }
+    for name, s in sig.items():
+        if s is None or not hasattr(lib, name):
+            continue
+        fn = getattr(lib, name)
+        fn.argtypes, fn.restype = s
+    return lib
+
+
+lib = _load()
+EXPORTED = [n for n in ("lb_abi_version", "lb_lora_linear_fwd", "lb_lora_wgrad",
+                        "lb_cast_rows_pad16", "lb_cast_weight", "lb_adamw_clip_step",
+                        "lb_refresh_shadows")]
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise LoraB200Error(f"{what} failed: {_STATUS.get(status, status)}")
+
+
+def dtype_code(torch_dtype):
+    import torch
+    if torch_dtype == torch.bfloat16:
+        return LB_BF16
+    if torch_dtype == torch.float16:
+        return LB_F16
+    if torch_dtype == torch.float32:
+        return LB_F32
+    raise LoraB200Error(f"unsupported dtype {torch_dtype}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,68 @@
+// Host-side TMA tensor-map encoding. cuTensorMapEncodeTiled is fetched through the runtime's
+// driver-entry-point query so the library has no link-time dependency on libcuda.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lb {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Row-major 2-D tensor [rows, cols] (cols contiguous), box = [box_rows, box_cols].
+// OOB reads are zero-filled, OOB writes clipped. swz128: the inner box extent must be 128 bytes.
+inline bool tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elem_bytes,
+                    uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows,
+                    bool swz128) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * static_cast<uint64_t>(elem_bytes)};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swz128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// NHWC activation [N, H, W, C] (C contiguous) viewed as a 4-D tensor {C, W, H, N};
+// box = {box_c, box_w, box_h, 1}. Used by the implicit-GEMM conv path: a (box_h x box_w) pixel
+// rectangle lands in shared memory as box_h*box_w rows of box_c channels (128 B each).
+inline bool tmap_nhwc(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elem_bytes,
+                      uint64_t C, uint64_t W, uint64_t H, uint64_t N, uint32_t box_c,
+                      uint32_t box_w, uint32_t box_h) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {C * static_cast<uint64_t>(elem_bytes),
+                           W * C * static_cast<uint64_t>(elem_bytes),
+                           H * W * C * static_cast<uint64_t>(elem_bytes)};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, dt, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace lb
