@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- SD1.5 LoRA-r4 512px training step (BASELINE.json configs[1]) on N x B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+  python bench.py --impl reference ...                     (the reference's CPU path, oracle port)
+
+One "step" = one full Dreambooth LoRA training step at bs = 1 per GPU: text encoder (48 LoRA
+sites) -> UNet (144 LoRA sites) forward, MSE, backward (dX, dA, dB; W frozen), gradient
+all-reduce over the LoRA arena, global-norm clip + AdamW. Synthetic latents / token ids and
+random-initialised SD1.5-shaped weights (no datasets or checkpoints offline).
+
+Prints ONE JSON line (rank 0). `value` = images/s with inputs resident in HBM; `e2e` = the same
+through the public step_host() call with pinned-host inputs (H2D) and a D2H loss read per step;
+`roofline` = the fused tcgen05 LoRA-linear kernel (all 384 fwd + dX launches of one step, real
+site shapes) timed live with CUDA events: algorithmic bytes / time vs the measured HBM peak;
+`cpu_baseline` = the oracle port of the reference's step on the host cores (rank 0, N = 1).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "sd15_lora_r4_512px_train_images_per_sec"
+UNIT = "images/s"
+WORKLOAD = "SD1.5 UNet+text_encoder LoRA rank=4 512x512 bf16 bs=1/GPU dreambooth step (configs[1])"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                  "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def build_models(device, dtype, seed=0, tiny=False):
+    from lora_b200.host.clip import build_text_encoder
+    from lora_b200.host.unet_sd15 import UNet2DConditionModel, UNetConfig
+    torch.manual_seed(seed)
+    with torch.device(device):
+        unet = UNet2DConditionModel(UNetConfig.tiny() if tiny else UNetConfig.sd15())
+        text = build_text_encoder(tiny=tiny)
+    unet.requires_grad_(False)
+    text.requires_grad_(False)
+    return unet.to(dtype), text.to(dtype)
+
+
+def site_shapes(model, tokens_by_module):
+    """(M, K, N, r, has_bias) for every LoraInjectedLinear of `model`; M from the recorded calls."""
+    out = []
+    for m in model.modules():
+        if type(m).__name__ == "LoraInjectedLinear":
+            out.append((tokens_by_module[id(m)], m.linear.in_features, m.linear.out_features, m.r,
+                        m.linear.bias is not None))
+    return out
+
+
+def fused_linear_bytes(M, K, N, r, bias, e=2):
+    """algorithmic bytes of one fused LoRA-linear launch (16-bit operands):
+    X + W + down + up + Y (+ bias fp32) (+ T fp32 [M,16] side output)."""
+    return e * (M * K + N * K + r * K + M * N) + 4 * N * r + (4 * N if bias else 0) + 4 * M * 16
+
+
+def roofline_sweep(trainer, shapes, iters=10):
+    """All fused-kernel launches of one step (fwd: X[M,K]->Y[M,N]; dX: gY[M,N]->dX[M,K]) with
+    private buffers per site, captured in one CUDA graph, timed with CUDA events."""
+    from lora_b200 import ops
+    dev = trainer.device
+    dt = trainer.cfg.compute_dtype
+    launches = []
+    total_bytes = 0
+    for (M, K, N, r, bias) in shapes:
+        for (m, k, n) in ((M, K, N), (M, N, K)):        # forward, then dX on the transposed weight
+            x = torch.randn(m, k, device=dev, dtype=dt)
+            w = torch.randn(n, k, device=dev, dtype=dt) * 0.02
+            a = torch.randn(r, k, device=dev)
+            b = torch.randn(n, r, device=dev) * 0.01
+            d16 = ops.cast_rows_pad16(a, k, 1, r, k, dt)
+            bb = torch.zeros(n, device=dev) if (bias and (m, k, n) == (M, K, N)) else None
+            launches.append((x, w, bb, d16, b, r))
+            total_bytes += fused_linear_bytes(m, k, n, r, bb is not None)
+
+    def run():
+        for (x, w, bb, d16, b, r) in launches:
+            ops.fused_linear(x, w, bb, d16, b, r, 1, None, 1.0, r, dt, True)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run(); run()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        run()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return total_bytes, ms, len(launches)
+
+
+def record_tokens(unet, text):
+    """Forward hooks: rows (tokens) seen by each LoRA linear in one step."""
+    seen = {}
+    hooks = []
+    for model in (unet, text):
+        for m in model.modules():
+            if type(m).__name__ == "LoraInjectedLinear":
+                hooks.append(m.register_forward_pre_hook(
+                    lambda mod, inp: seen.__setitem__(id(mod), inp[0].numel() // inp[0].shape[-1])))
+    return seen, hooks
+
+
+def run_native(args):
+    import torch.distributed as dist
+    from lora_b200 import ops
+    import lora_b200 as L
+    from lora_b200.train import LoraTrainStep, StepConfig
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    dt = torch.bfloat16
+    res = args.res
+    L_lat = res // 8
+    unet, text = build_models(dev, dt, seed=0, tiny=args.tiny)
+    L.inject_trainable_lora(unet, r=args.rank)
+    L.inject_trainable_lora(text, target_replace_module={"CLIPAttention"}, r=args.rank)
+    # reference init has up = 0 (lora.py:51); give the up factors small non-zero values so the
+    # LoRA branch and all three gradients are numerically exercised
+    g = torch.Generator(device=dev).manual_seed(1)
+    for m in list(unet.modules()) + list(text.modules()):
+        if type(m).__name__ == "LoraInjectedLinear":
+            m.lora_up.weight.data.normal_(0.0, 0.01, generator=g)
+
+    cfg = StepConfig(compute_dtype=dt, use_cuda_graph=not args.no_graph)
+    seq = 77
+    trainer = LoraTrainStep(unet, text, cfg, latent_shape=(1, 4, L_lat, L_lat), seq_len=seq, device=dev)
+    vocab = text.config.vocab_size
+    torch.manual_seed(1234 + rank)
+    n_data = 4
+    host_lat = [(torch.randn(1, 4, L_lat, L_lat) * 0.18215).pin_memory() for _ in range(n_data)]
+    host_ids = [torch.randint(0, vocab, (1, seq)).pin_memory() for _ in range(n_data)]
+    trainer.latents.copy_(host_lat[0]); trainer.input_ids.copy_(host_ids[0])
+
+    seen, hooks = record_tokens(unet, text)
+    ops.LAUNCH_COUNT = 0
+    trainer._body()                      # one eager step: records tokens per site + launch count
+    launches_per_step = ops.LAUNCH_COUNT
+    if args.profile_steps:               # ncu launch-list mode: a few eager steps, nothing else
+        for _ in range(args.profile_steps):
+            trainer._body()
+        torch.cuda.synchronize()
+        return None
+    for h in hooks:
+        h.remove()
+    torch.cuda.synchronize()
+    trainer.prepare()                    # warm-up + CUDA-graph capture
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing (value)
+    for _ in range(max(args.warmup, 3)):
+        trainer.step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        trainer.step_device()
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    loss_dev = float(trainer.loss.item())
+
+    # ---------------- end-to-end timing (public step_host API, pinned host inputs, D2H loss)
+    for i in range(3):
+        trainer.step_host(host_lat[i % n_data], host_ids[i % n_data])
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for i in range(args.steps):
+        hl = trainer.step_host(host_lat[i % n_data], host_ids[i % n_data])
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    loss_e2e = float(hl.item())
+
+    t = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+
+    out = None
+    if rank == 0:
+        shapes = site_shapes(unet, seen) + site_shapes(text, seen)
+        hbm_peak, peak_src = load_peaks()
+        rb, rms, n_l = roofline_sweep(trainer, shapes)
+        achieved = rb / (rms * 1e-3) / 1e9
+        value = world * args.steps / (ms_dev * 1e-3)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic latents/token ids, random-init SD1.5-shaped weights",
+            "config": {"workload": WORKLOAD if not args.tiny else "TINY smoke config (not a bench)",
+                       "resolution": res, "rank": args.rank, "global_batch": world,
+                       "lora_sites": len(shapes), "lora_params": trainer.arena.n_params,
+                       "parallelism": f"dp{world}", "cuda_graph": trainer.graph is not None,
+                       "graph_error": trainer.graph_error,
+                       "l2": "working set per step (>=1.7 GB frozen weights + activations) exceeds the 126 MB L2; no explicit flush",
+                       "loss": loss_dev},
+            "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": trainer.h2d_bytes(), "d2h_bytes_per_step": trainer.d2h_bytes(),
+                    "loss": loss_e2e},
+            "gpu_launches": int(launches_per_step * args.steps * 2),
+            "gpu_launches_per_step": int(launches_per_step),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "fused_lora_linear_kernel (fwd + dX launches of one step)",
+                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None,
+                         "launches": n_l, "algorithmic_bytes": rb, "ms_per_sweep": rms,
+                         "avg_launch_us": rms * 1e3 / n_l,
+                         "share_of_step": rms / (ms_dev / args.steps), "peak_source": peak_src},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_reference(res, args.rank, budget_s=args.cpu_budget, tiny=args.tiny)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference(res, rank_r, budget_s=30.0, max_steps=None, warmup=1, tiny=False):
+    """The reference's own path on the host cores: oracle port (oracle/ref_modules.py,
+    oracle/ref_step.py: torch-eager fp32 LoRA modules + torch.optim.AdamW + clip_grad_norm_) in
+    the same SD1.5-shaped host models, full steps at the bench resolution."""
+    from oracle.ref_modules import ref_inject
+    from oracle.ref_step import RefDreamboothStep
+    from lora_b200.host.ddpm import DDPMNoiser
+    unet, text = build_models("cpu", torch.float32, seed=0, tiny=tiny)
+    us = ref_inject(unet, {"CrossAttention", "Attention", "GEGLU"}, r=rank_r)
+    ts = ref_inject(text, {"CLIPAttention"}, r=rank_r)
+    stepper = RefDreamboothStep(unet, text, DDPMNoiser(), us, ts)
+    L_lat = res // 8
+    torch.manual_seed(1234)
+    lat = torch.randn(1, 4, L_lat, L_lat) * 0.18215
+    ids = torch.randint(0, text.config.vocab_size, (1, 77))
+    cores = torch.get_num_threads()
+    t_w = time.perf_counter()
+    for _ in range(warmup):
+        stepper.step(lat, ids)
+    t_w = (time.perf_counter() - t_w) / max(warmup, 1)
+    n = max(1, int(budget_s / max(t_w, 1e-3)))
+    if max_steps is not None:
+        n = min(n, max_steps)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        loss = stepper.step(lat, ids)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} full training step(s) at {res}x{res}, bs=1, fp32, torch eager "
+                      f"{torch.__version__}, after {warmup} warm-up; os.cpu_count()={os.cpu_count()}",
+            "ms_per_step": dt / n * 1e3, "steps": n, "loss": float(loss)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    cb = cpu_reference(args.res, args.rank, budget_s=args.cpu_budget * 6, max_steps=args.steps,
+                       warmup=min(max(args.warmup, 1), 2), tiny=args.tiny)
+    return {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": cb["steps"], "warmup": min(max(args.warmup, 1), 2),
+        "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic latents/token ids, random-init SD1.5-shaped weights",
+        "config": {"workload": WORKLOAD, "resolution": args.res, "rank": args.rank,
+                   "note": "reference = pure-Python lora_diffusion on torch eager; it cannot be imported on this box "
+                           "(diffusers/accelerate/fire absent), so its step is the oracle port on the host cores"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--res", type=int, default=512)
+    ap.add_argument("--rank", type=int, default=4)
+    ap.add_argument("--tiny", action="store_true", help="toy widths (smoke only, not a bench)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=0, help="run N eager steps and exit (for ncu)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU-baseline work")
+    args = ap.parse_args()
+    out = run_reference(args) if args.impl == "reference" else run_native(args)
+    if out is not None:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

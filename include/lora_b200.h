@@ -78,8 +78,9 @@ int lb_cast_weight(const void* src, int src_dtype, void* dst16, void* dstT16, in
  *   total = inv_world * ||g||_2 ; coef = min(1, max_norm / (total + 1e-6))  (max_norm <= 0: no clip)
  *   g' = g * inv_world * coef ; decoupled weight decay ; Adam moments ; bias correction with
  *   t = ++(*step_dev) ; g is zeroed for the next step ; *gnorm_out = total.
- * Elements [group_off[i], group_off[i+1]) use lr_dev[i] (device array, so a captured graph sees
- * scheduler updates). partials: scratch of >= 1024 floats.
+ * Elements [group_off[i], group_off[i+1]) use lr_dev[i]; group_off is a HOST array of
+ * n_groups+1 offsets (n_groups <= 8), lr_dev a DEVICE array (so a captured graph sees scheduler
+ * updates), step_dev a DEVICE int. partials: device scratch of >= 1024 floats.
  * Replaces clip_grad_norm_ + torch.optim.AdamW.step + zero_grad,
  * training_scripts/train_lora_dreambooth.py:878-888 and lora_diffusion/cli_lora_pti.py:606-609.
  */
@@ -88,9 +89,10 @@ int lb_adamw_clip_step(float* p, float* g, float* m, float* v, long long n,
                        float beta2, float eps, float weight_decay, float max_norm, float inv_world,
                        int* step_dev, float* partials, float* gnorm_out, void* stream);
 
-/* Batched 16-bit shadow refresh after an optimizer step: for every table entry e
- *   dst16_base[e.dst_off + j*e.C + c] = (j < e.r) ? p[e.src_off + j*e.src_rs + c*e.src_cs] : 0
- * table: device array of n_entries x 6 long long {src_off, src_rs, src_cs, r, C, dst_off}. */
+/* Batched 16-bit shadow refresh after an optimizer step: for every table entry e, j < 16, c < e.C
+ *   dst16_base[e.dst_off + j*e.dst_rs + c] = (j < e.r) ? p[e.src_off + j*e.src_rs + c*e.src_cs] : 0
+ * table: DEVICE array of n_entries x 7 long long {src_off, src_rs, src_cs, r, C, dst_off, dst_rs}.
+ * (conv down factors use one entry per filter tap so that K is ordered tap-major, channel-minor) */
 int lb_refresh_shadows(const float* p, const long long* table, int n_entries, int max_C,
                        void* dst16_base, int out_dtype, void* stream);
 

@@ -102,16 +102,16 @@ __global__ void cast_rows_pad16_kernel(const float* __restrict__ src, long long 
 __global__ void refresh_shadows_kernel(const float* __restrict__ p,
                                        const long long* __restrict__ table,
                                        uint16_t* __restrict__ dst_base, int fmt) {
-  const long long* e = table + static_cast<size_t>(blockIdx.y) * 6;
+  const long long* e = table + static_cast<size_t>(blockIdx.y) * 7;
   const long long src_off = e[0], rs = e[1], cs = e[2];
   const int r = static_cast<int>(e[3]), C = static_cast<int>(e[4]);
-  const long long dst_off = e[5];
+  const long long dst_off = e[5], dst_rs = e[6];
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
 #pragma unroll
   for (int j = 0; j < 16; ++j) {
     const float x = (j < r) ? p[src_off + j * rs + c * cs] : 0.f;
-    dst_base[dst_off + static_cast<size_t>(j) * C + c] = to16(x, fmt);
+    dst_base[dst_off + j * dst_rs + c] = to16(x, fmt);
   }
 }
 

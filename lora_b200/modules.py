@@ -144,7 +144,7 @@ class _FusedLoraLinearFn(torch.autograd.Function):
         x2d = x.reshape(-1, K)
         if x2d.dtype != cdt or not x2d.is_contiguous():
             x2d = x2d.to(cdt).contiguous()
-        need_bwd = torch.is_grad_enabled() and (x.requires_grad or A.requires_grad or B.requires_grad)
+        need_bwd = any(ctx.needs_input_grad[:3])
         w16, _ = st.frozen(lin.weight, cdt, need_t=False)
         b32 = st.bias32(lin.bias)
         A32 = _fp32_master(A)

@@ -11,6 +11,12 @@ from . import _C
 from ._C import check, dtype_code, ptr, stream_ptr
 
 R_PAD = 16
+LAUNCH_COUNT = 0  # kernels of liblora_b200.so enqueued through this process (bench.py reads it)
+
+
+def _count(n: int = 1):
+    global LAUNCH_COUNT
+    LAUNCH_COUNT += n
 
 
 def _req_cuda(*ts):
@@ -25,6 +31,7 @@ def cast_rows_pad16(src: torch.Tensor, rs: int, cs: int, r: int, C: int, dtype) 
     out = torch.empty((R_PAD, C), device=src.device, dtype=dtype)
     check(_C.lib.lb_cast_rows_pad16(ptr(src), rs, cs, ptr(out), r, C, dtype_code(dtype),
                                     stream_ptr()), "lb_cast_rows_pad16")
+    _count()
     return out
 
 
@@ -41,6 +48,7 @@ def cast_weight(w: torch.Tensor, dtype, want_plain: bool, want_t: bool):
     wt = torch.empty((C, R), device=w.device, dtype=dtype) if want_t else None
     check(_C.lib.lb_cast_weight(ptr(w), dtype_code(w.dtype), ptr(plain), ptr(wt), R, C,
                                 dtype_code(dtype), stream_ptr()), "lb_cast_weight")
+    _count()
     return plain, wt
 
 
@@ -60,6 +68,7 @@ def fused_linear(x2d: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tens
                                     up_rs, up_cs, ptr(diag), float(scale), ptr(y), ptr(t),
                                     M, K, N, r, dtype_code(x2d.dtype), dtype_code(out_dtype),
                                     stream_ptr()), "lb_lora_linear_fwd")
+    _count()
     return y, t
 
 
@@ -72,3 +81,4 @@ def wgrad(S: torch.Tensor, V: torch.Tensor, diag: Optional[torch.Tensor], scale:
     assert out.dtype == torch.float32
     check(_C.lib.lb_lora_wgrad(ptr(S), ptr(V), ptr(diag), float(scale), ptr(out), out_js, out_cs,
                                M, C, r, dtype_code(S.dtype), stream_ptr()), "lb_lora_wgrad")
+    _count()

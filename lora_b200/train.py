@@ -1,0 +1,147 @@
+"""Training-step engine: the step loop of the reference's trainers, restated around the fused
+LoRA path and captured as ONE CUDA graph.
+
+Restates (diffusers / accelerate are not installed, so the scripts themselves cannot run):
+  training_scripts/train_lora_dreambooth.py:811-888  -- Dreambooth step (noise, timestep,
+      add_noise, text encoder, UNet, MSE, backward, clip_grad_norm_(1.0), AdamW, zero_grad)
+  lora_diffusion/cli_lora_pti.py:260-370, 585-617     -- PTI LoRA-tuning phase (same step with
+      t_mutliplier and mean([1,2,3]).mean() reduction)
+Differences by design: LoRA factors/grads/moments live in a LoraArena, the
+DDP all-reduce + clip + AdamW + zero_grad are one NCCL call and two kernels, and steady-state
+steps are CUDA-graph replays (no Python, no launch gaps, no host sync).
+"""
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .arena import LoraArena
+from .host.ddpm import DDPMNoiser
+
+
+@dataclass
+class StepConfig:
+    # defaults = training_scripts/train_lora_dreambooth.py:364-387 and run_lora_db_w_text.sh:6-20
+    learning_rate: float = 1e-4
+    learning_rate_text: float = 5e-5
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.999
+    adam_weight_decay: float = 1e-2
+    adam_epsilon: float = 1e-8
+    max_grad_norm: float = 1.0
+    train_text_encoder: bool = True
+    t_multiplier: float = 1.0          # cli_lora_pti.py:598 uses 0.8 in the tuning phase
+    compute_dtype: torch.dtype = torch.bfloat16
+    use_cuda_graph: bool = True
+    graph_warmup: int = 3
+    # accelerate-style mixed precision (fp32 frozen weights + torch.autocast), the reference's
+    # own configuration (train_lora_dreambooth.py:489-494). None: run in the models' own dtype.
+    autocast_dtype: Optional[torch.dtype] = None
+
+
+class LoraTrainStep:
+    """One data-parallel replica of the LoRA fine-tuning step (bs = latents.shape[0] per GPU)."""
+
+    def __init__(self, unet: nn.Module, text_encoder: nn.Module, cfg: StepConfig,
+                 latent_shape=(1, 4, 64, 64), seq_len: int = 77, device=None):
+        self.cfg = cfg
+        self.unet, self.text_encoder = unet, text_encoder
+        self.device = torch.device(device or "cuda")
+        groups = [(unet, cfg.learning_rate)]
+        if cfg.train_text_encoder:
+            groups.append((text_encoder, cfg.learning_rate_text))
+        self.arena = LoraArena(groups, compute_dtype=cfg.compute_dtype, device=self.device)
+        self.noiser = DDPMNoiser(device=self.device)
+        self.model_dtype = next(unet.parameters()).dtype
+        # static step I/O (graph-stable addresses)
+        self.latents = torch.zeros(latent_shape, device=self.device, dtype=torch.float32)
+        self.input_ids = torch.zeros((latent_shape[0], seq_len), device=self.device, dtype=torch.long)
+        self.loss = torch.zeros((), device=self.device, dtype=torch.float32)
+        # pinned host mirrors for the end-to-end path
+        self.h_latents = torch.zeros(latent_shape, dtype=torch.float32).pin_memory()
+        self.h_input_ids = torch.zeros((latent_shape[0], seq_len), dtype=torch.long).pin_memory()
+        self.h_loss = torch.zeros((), dtype=torch.float32).pin_memory()
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_error: Optional[str] = None
+        self._world = 1
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            self._world = dist.get_world_size()
+        self.unet.train()
+        self.text_encoder.train()
+
+    # ------------------------------------------------------------------ the step body
+    def _body(self):
+        cfg = self.cfg
+        lat = self.latents
+        bsz = lat.shape[0]
+        noise = torch.randn_like(lat)
+        t_max = int(self.noiser.num_train_timesteps * cfg.t_multiplier)
+        timesteps = torch.randint(0, t_max, (bsz,), device=lat.device).long()
+        noisy = self.noiser.add_noise(lat, noise, timesteps)
+        ac = (torch.autocast("cuda", dtype=cfg.autocast_dtype) if cfg.autocast_dtype is not None
+              else torch.autocast("cuda", enabled=False))
+        with ac:
+            if cfg.train_text_encoder:
+                ehs = self.text_encoder(self.input_ids)[0]
+            else:
+                with torch.no_grad():
+                    ehs = self.text_encoder(self.input_ids)[0]
+            pred = self.unet(noisy.to(self.model_dtype), timesteps, ehs.to(self.model_dtype)).sample
+        loss = F.mse_loss(pred.float(), noise.float(), reduction="mean")
+        loss.backward()
+        self.arena.allreduce_grads()
+        self.arena.step(cfg.adam_beta1, cfg.adam_beta2, cfg.adam_epsilon, cfg.adam_weight_decay,
+                        cfg.max_grad_norm, world_size=self._world)
+        self.loss.copy_(loss.detach())
+
+    def _capture(self):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self.cfg.graph_warmup):
+                self._body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._body()
+        self.graph = g
+
+    # ------------------------------------------------------------------ public API
+    def prepare(self):
+        """Warm up and (optionally) capture. Counts graph_warmup + 1 optimizer steps."""
+        if self.cfg.use_cuda_graph and self.graph is None and self.graph_error is None:
+            try:
+                self._capture()
+            except Exception as e:  # capture refused (e.g. a host sync inside the host model)
+                self.graph_error = f"{type(e).__name__}: {e}"
+                self.graph = None
+                torch.cuda.synchronize()
+
+    def step_device(self) -> torch.Tensor:
+        """One step on inputs already resident in self.latents / self.input_ids."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+        return self.loss
+
+    def step_host(self, latents_cpu: torch.Tensor, input_ids_cpu: torch.Tensor) -> torch.Tensor:
+        """End-to-end step from pinned host memory: H2D inputs, step, D2H loss (async, returns the
+        pinned loss buffer; synchronise the stream before reading it)."""
+        self.h_latents.copy_(latents_cpu)
+        self.h_input_ids.copy_(input_ids_cpu)
+        self.latents.copy_(self.h_latents, non_blocking=True)
+        self.input_ids.copy_(self.h_input_ids, non_blocking=True)
+        self.step_device()
+        self.h_loss.copy_(self.loss, non_blocking=True)
+        return self.h_loss
+
+    def h2d_bytes(self) -> int:
+        return self.h_latents.numel() * 4 + self.h_input_ids.numel() * 8
+
+    def d2h_bytes(self) -> int:
+        return 4

@@ -1,0 +1,69 @@
+"""ORACLE (test infrastructure only): the reference's Dreambooth training step in plain PyTorch.
+
+Restates training_scripts/train_lora_dreambooth.py:651-676 (AdamW param groups) and :811-888
+(the step) with the stock torch pieces the reference itself calls -- torch.optim.AdamW,
+torch.nn.utils.clip_grad_norm_, F.mse_loss -- over RefLoraSite modules (oracle/ref_modules.py).
+The host UNet / text encoder / noiser objects are passed in by the caller (tests, bench.py);
+this file imports nothing from the product package.
+"""
+import itertools
+from typing import List, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+class RefDreamboothStep:
+    def __init__(self, unet, text_encoder, noiser, unet_sites: List, text_sites: Optional[List],
+                 lr=1e-4, lr_text=5e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8,
+                 max_grad_norm=1.0, t_multiplier: float = 1.0, autocast_dtype=None):
+        self.unet, self.text_encoder, self.noiser = unet, text_encoder, noiser
+        self.max_grad_norm = max_grad_norm
+        self.t_multiplier = t_multiplier
+        self.autocast_dtype = autocast_dtype
+        self.train_text = bool(text_sites)
+
+        def factors(sites):  # reference order per site: up then down (lora.py:298-299)
+            return list(itertools.chain(*[(s.up, s.down) for s in sites]))
+
+        for p in itertools.chain(unet.parameters(), text_encoder.parameters()):
+            p.requires_grad_(False)
+        self.unet_params = factors(unet_sites)
+        self.text_params = factors(text_sites) if text_sites else []
+        for p in self.unet_params + self.text_params:
+            p.requires_grad_(True)
+        groups = [{"params": self.unet_params, "lr": lr}]
+        if self.text_params:
+            groups.append({"params": self.text_params, "lr": lr_text})
+        self.opt = torch.optim.AdamW(groups, lr=lr, betas=betas, weight_decay=weight_decay, eps=eps)
+        unet.train()
+        text_encoder.train()
+
+    def forward_loss(self, latents, input_ids, noise, timesteps):
+        noisy = self.noiser.add_noise(latents, noise, timesteps)
+        dev = latents.device.type
+        ctx = torch.autocast(dev, dtype=self.autocast_dtype) if self.autocast_dtype else torch.autocast(dev, enabled=False)
+        with ctx:
+            if self.train_text:
+                ehs = self.text_encoder(input_ids)[0]
+            else:
+                with torch.no_grad():
+                    ehs = self.text_encoder(input_ids)[0]
+            mdt = next(self.unet.parameters()).dtype
+            pred = self.unet(noisy.to(mdt), timesteps, ehs.to(mdt)).sample
+        return F.mse_loss(pred.float(), noise.float(), reduction="mean")
+
+    def step(self, latents, input_ids, noise=None, timesteps=None):
+        """noise/timesteps may be supplied (parity tests); otherwise drawn like the reference."""
+        if noise is None:
+            noise = torch.randn_like(latents)
+        if timesteps is None:
+            t_max = int(self.noiser.num_train_timesteps * self.t_multiplier)
+            timesteps = torch.randint(0, t_max, (latents.shape[0],), device=latents.device).long()
+        loss = self.forward_loss(latents, input_ids, noise, timesteps)
+        loss.backward()
+        if self.max_grad_norm:
+            torch.nn.utils.clip_grad_norm_(self.unet_params + self.text_params, self.max_grad_norm)
+        self.opt.step()
+        self.opt.zero_grad()
+        return loss.detach()
