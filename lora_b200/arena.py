@@ -172,11 +172,8 @@ class LoraArena:
 
     def allreduce_grads(self):
         """The one data-path collective: sum of the flat gradient buffer over NVLink/NVSwitch."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.g, op=dist.ReduceOp.SUM)
-            return dist.get_world_size()
-        return 1
+        from .dist import allreduce_sum_
+        return allreduce_sum_(self.g)
 
     def step(self, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, max_norm=1.0,
              world_size: int = 1):

@@ -95,8 +95,18 @@ def _finish_site(parent, name, new, loras, params, names):
     params.append(site.lora_up.parameters())
     params.append(site.lora_down.parameters())
     if loras is not None:
-        site.lora_up.weight = loras.pop(0)
-        site.lora_down.weight = loras.pop(0)
+        # The reference assigns the list entries as they are (lora.py:302-303), which only works
+        # when the .pt holds nn.Parameter objects; files written by save_lora_weight hold plain
+        # fp16 tensors and make that assignment raise TypeError. Accept both: plain tensors are
+        # wrapped (and cast to the site's dtype, as monkeypatch_or_replace_lora does, lora.py:706-711).
+        like = site.lora_up.weight
+        up, down = loras.pop(0), loras.pop(0)
+        if not isinstance(up, nn.Parameter):
+            up = nn.Parameter(up.detach().to(like.device, like.dtype))
+        if not isinstance(down, nn.Parameter):
+            down = nn.Parameter(down.detach().to(like.device, like.dtype))
+        site.lora_up.weight = up
+        site.lora_down.weight = down
     site.lora_up.weight.requires_grad = True
     site.lora_down.weight.requires_grad = True
     names.append(name)

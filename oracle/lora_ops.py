@@ -145,3 +145,28 @@ def collapse_delta(A, B, alpha: float = 1.0):
     """lora_diffusion/lora.py:646-669: W += alpha * (up @ down) (conv: flattened)."""
     A, B = _f(A), _f(B)
     return alpha * (B.flatten(1) @ A.flatten(1))
+
+
+def lora_conv2d_backward(gy, x, W, A, B, scale: float, stride=1, padding=0, dilation=1, diag=None):
+    """Autograd of lora.py:130-135 with the base conv frozen: returns (dX, dA, dB), written with
+    the explicit transposed-convolution / weight-gradient operators (float64, no autograd graph).
+
+        gU = scale * gY ;  dB[o,j] = sum_{n,h,w} gU[n,o,h,w] * (S t)[n,j,h,w]   (t = conv(x, A))
+        dT = S^T (B^T gU)                      (1x1 up-projection transposed, then the selector)
+        dA = conv_weight_grad(x, dT) ;  dX = conv_input_grad(gY, W) + conv_input_grad(dT, A)
+    """
+    from torch.nn import grad as G
+    gy, x, W, A, B = _f(gy), _f(x), _f(W), _f(A), _f(B)
+    r = A.shape[0]
+    S = selector_matrix(diag, r)
+    t = _conv2d_naive(x, A, stride, padding, dilation)
+    t_sel = torch.einsum("nchw,dc->ndhw", t, S)
+    gu = gy * scale
+    B2 = B.reshape(B.shape[0], r)
+    dB = torch.einsum("nohw,njhw->oj", gu, t_sel).reshape(B.shape)
+    dT = torch.einsum("nohw,oj->njhw", gu, B2)
+    dT = torch.einsum("njhw,jc->nchw", dT, S)
+    dA = G.conv2d_weight(x, A.shape, dT, stride, padding, dilation, 1)
+    dX = G.conv2d_input(x.shape, W, gy, stride, padding, dilation, 1) + \
+        G.conv2d_input(x.shape, A, dT, stride, padding, dilation, 1)
+    return dX, dA, dB

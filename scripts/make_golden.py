@@ -1,0 +1,243 @@
+"""Generate tests/golden/* by RUNNING THE REAL REFERENCE (/root/reference/lora_diffusion/lora.py
+and cli_svd.py, loaded by file path because the package import needs fire/diffusers) on small
+seeded inputs. Run in the build container (the reference tree does not exist on the GPU box):
+
+    python scripts/make_golden.py
+
+Outputs (all small, committed):
+  golden/ops_linear.pt, ops_conv.pt     operator forward + autograd grads (fp32, CPU)
+  golden/ctor_rng.pt                    lora_down init values after manual_seed(0) (RNG parity)
+  golden/inject_tiny.json               site names/order from the reference's inject on the tiny
+                                        host UNet / CLIP (default + extended target sets)
+  golden/tiny_saved.safetensors         save_safeloras output of the reference on the tiny models
+  golden/example_loras_manifest.json    keys / shapes / dtypes / metadata / sha256 of the ten
+                                        fixture files in /root/reference/example_loras
+  golden/svd_distill.pt                 cli_svd.overwrite_base outputs on small matrices
+  golden/adamw_clip.pt                  clip_grad_norm_ + torch.optim.AdamW trajectories
+"""
+import hashlib
+import importlib.util
+import json
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def load_ref_lora():
+    spec = importlib.util.spec_from_file_location("ref_lora", f"{REF}/lora_diffusion/lora.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_ref_svd(ref_lora):
+    """cli_svd.py imports fire and diffusers at module top; stub them, and satisfy its relative
+    import `.lora` with the already-loaded reference module."""
+    pkg = types.ModuleType("lora_diffusion_ref")
+    pkg.__path__ = [f"{REF}/lora_diffusion"]
+    sys.modules["lora_diffusion_ref"] = pkg
+    sys.modules["lora_diffusion_ref.lora"] = ref_lora
+    sys.modules.setdefault("fire", types.ModuleType("fire"))
+    d = types.ModuleType("diffusers")
+    d.StableDiffusionPipeline = object
+    sys.modules.setdefault("diffusers", d)
+    spec = importlib.util.spec_from_file_location("lora_diffusion_ref.cli_svd", f"{REF}/lora_diffusion/cli_svd.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def gen_ops(R):
+    cases = []
+    for i, (M, K, N, r, bias, scale, diag) in enumerate([
+            (24, 16, 24, 4, True, 1.0, False), (10, 32, 8, 1, False, 0.5, False),
+            (33, 40, 48, 8, True, 1.7, True), (7, 64, 64, 16, True, 0.25, True)]):
+        torch.manual_seed(100 + i)
+        m = R.LoraInjectedLinear(K, N, bias, r=r, dropout_p=0.0, scale=scale)
+        m.lora_up.weight.data.normal_(0, 0.1)
+        d = None
+        if diag:
+            d = torch.rand(r) + 0.5
+            m.set_selector_from_diag(d)
+        x = torch.randn(2, M, K, requires_grad=True)
+        y = m(x)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        cases.append(dict(x=x.detach(), W=m.linear.weight.detach(), b=None if not bias else m.linear.bias.detach(),
+                          A=m.lora_down.weight.detach(), B=m.lora_up.weight.detach(), scale=scale, diag=d,
+                          y=y.detach(), gy=gy, dX=x.grad, dA=m.lora_down.weight.grad, dB=m.lora_up.weight.grad,
+                          dW_is_none=True))
+    torch.save(cases, f"{OUT}/ops_linear.pt")
+
+    conv = []
+    for i, (Cin, Cout, k, pad, r, bias, scale, HW) in enumerate([
+            (8, 16, 3, 1, 4, True, 1.0, 6), (16, 8, 1, 0, 4, False, 0.5, 5), (12, 12, 3, 1, 8, True, 2.0, 9)]):
+        torch.manual_seed(200 + i)
+        m = R.LoraInjectedConv2d(Cin, Cout, k, 1, pad, 1, 1, bias, r=r, dropout_p=0.0, scale=scale)
+        m.lora_up.weight.data.normal_(0, 0.1)
+        x = torch.randn(2, Cin, HW, HW, requires_grad=True)
+        y = m(x)
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        conv.append(dict(x=x.detach(), W=m.conv.weight.detach(), b=None if not bias else m.conv.bias.detach(),
+                         A=m.lora_down.weight.detach(), B=m.lora_up.weight.detach(), scale=scale, padding=pad,
+                         y=y.detach(), gy=gy, dX=x.grad, dA=m.lora_down.weight.grad, dB=m.lora_up.weight.grad))
+    torch.save(conv, f"{OUT}/ops_conv.pt")
+
+    # dropout statistics are not golden-able (Philox stream); keep the p>0 eval-mode identity
+    torch.manual_seed(7)
+    m = R.LoraInjectedLinear(16, 16, False, r=4, dropout_p=0.1)
+    m.lora_up.weight.data.normal_(0, 0.1)
+    m.eval()
+    x = torch.randn(5, 16)
+    torch.save(dict(x=x, W=m.linear.weight.detach(), A=m.lora_down.weight.detach(), B=m.lora_up.weight.detach(),
+                    y_eval=m(x).detach()), f"{OUT}/ops_dropout_eval.pt")
+
+
+def gen_ctor_rng(R):
+    out = {}
+    torch.manual_seed(0)
+    m = R.LoraInjectedLinear(16, 24, True, r=4)
+    out["linear_down"] = m.lora_down.weight.detach().clone()
+    out["linear_next_rand"] = torch.rand(3)
+    torch.manual_seed(0)
+    c = R.LoraInjectedConv2d(8, 12, 3, 1, 1, r=4)
+    out["conv_down"] = c.lora_down.weight.detach().clone()
+    out["conv_next_rand"] = torch.rand(3)
+    torch.save(out, f"{OUT}/ctor_rng.pt")
+
+
+def gen_inject(R):
+    from lora_b200.host.clip import build_text_encoder
+    from lora_b200.host.unet_sd15 import UNet2DConditionModel, UNetConfig
+    res = {}
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel(UNetConfig.tiny())
+    _, names = R.inject_trainable_lora(unet, r=4)
+    res["unet_default_names"] = names
+    res["unet_default_shapes"] = [[list(m.lora_up.weight.shape), list(m.lora_down.weight.shape)]
+                                  for m in unet.modules() if m.__class__.__name__.startswith("LoraInjected")]
+    torch.manual_seed(0)
+    unet2 = UNet2DConditionModel(UNetConfig.tiny())
+    _, names2 = R.inject_trainable_lora_extended(unet2, r=4)
+    res["unet_extended_names"] = names2
+    res["unet_extended_kinds"] = [m.__class__.__name__ for m in unet2.modules()
+                                  if m.__class__.__name__.startswith("LoraInjected")]
+    res["unet_extended_shapes"] = [[list(m.lora_up.weight.shape), list(m.lora_down.weight.shape)]
+                                   for m in unet2.modules() if m.__class__.__name__.startswith("LoraInjected")]
+    torch.manual_seed(0)
+    te = build_text_encoder(tiny=True)
+    _, names3 = R.inject_trainable_lora(te, target_replace_module={"CLIPAttention"}, r=4)
+    res["text_names"] = names3
+    # a saved file from the reference, with non-trivial factors and scale
+    g = torch.Generator().manual_seed(5)
+    for mdl in (unet, te):
+        for m in mdl.modules():
+            if m.__class__.__name__ == "LoraInjectedLinear":
+                m.lora_up.weight.data.normal_(0, 0.05, generator=g)
+    R.tune_lora_scale(unet, 0.5)
+    R.save_safeloras_with_embeds({"unet": (unet, R.DEFAULT_TARGET_REPLACE),
+                                  "text_encoder": (te, R.TEXT_ENCODER_DEFAULT_TARGET_REPLACE)},
+                                 {"<s1>": torch.arange(48, dtype=torch.float32)},
+                                 f"{OUT}/tiny_saved.safetensors")
+    # the raw factors that produced it (so the test can rebuild the same state with our API)
+    raw = {"unet": [], "text_encoder": []}
+    for key, mdl in (("unet", unet), ("text_encoder", te)):
+        for m in mdl.modules():
+            if m.__class__.__name__ == "LoraInjectedLinear":
+                raw[key].append((m.lora_up.weight.detach().clone(), m.lora_down.weight.detach().clone()))
+    torch.save(raw, f"{OUT}/tiny_saved_raw.pt")
+    json.dump(res, open(f"{OUT}/inject_tiny.json", "w"), indent=1)
+
+
+def gen_manifest(R):
+    from safetensors import safe_open
+    man = {}
+    d = f"{REF}/example_loras"
+    for fn in sorted(os.listdir(d)):
+        if not fn.endswith(".safetensors"):
+            continue
+        f = safe_open(f"{d}/{fn}", framework="pt", device="cpu")
+        ent = {"metadata": f.metadata(), "tensors": {}}
+        for k in sorted(f.keys()):
+            t = f.get_tensor(k)
+            ent["tensors"][k] = [list(t.shape), str(t.dtype).replace("torch.", ""),
+                                 hashlib.sha256(t.contiguous().view(torch.uint8).numpy().tobytes()).hexdigest()[:16]]
+        parsed = R.parse_safeloras(f)
+        ent["parsed"] = {name: {"n_weights": len(w), "ranks": r, "targets": sorted(t)}
+                         for name, (w, r, t) in parsed.items()}
+        ent["embeds"] = sorted(R.parse_safeloras_embeds(f).keys())
+        man[fn] = ent
+    json.dump(man, open(f"{OUT}/example_loras_manifest.json", "w"))
+
+
+def gen_svd(R):
+    S = load_ref_svd(R)
+    out = []
+    for i, (N, K, rank, conv) in enumerate([(48, 32, 4, False), (24, 64, 8, False), (16, 8, 4, True)]):
+        torch.manual_seed(300 + i)
+
+        class Holder(nn.Module):
+            def __init__(self):
+                super().__init__()
+                if conv:
+                    self.m = R.LoraInjectedConv2d(K, N, 3, 1, 1, r=rank)
+                else:
+                    self.m = R.LoraInjectedLinear(K, N, False, r=rank)
+
+            @property
+            def device(self):
+                return torch.device("cpu")
+
+            @property
+            def dtype(self):
+                return torch.float32
+
+        base, tuned = Holder(), Holder()
+        wb = (base.m.conv if conv else base.m.linear).weight
+        wt = (tuned.m.conv if conv else tuned.m.linear).weight
+        low = torch.randn(N, rank) @ torch.randn(rank, wb[0].numel()) * 0.02
+        wt.data = wb.data + low.reshape(wb.shape) + torch.randn_like(wb) * 1e-3
+        S.overwrite_base(base, tuned, rank=rank, clamp_quantile=0.99)
+        out.append(dict(Wb=wb.detach().clone(), Wt=wt.detach().clone(), rank=rank, conv=conv, q=0.99,
+                        up=base.m.lora_up.weight.detach().clone(), down=base.m.lora_down.weight.detach().clone()))
+    torch.save(out, f"{OUT}/svd_distill.pt")
+
+
+def gen_adamw():
+    torch.manual_seed(400)
+    ps = [torch.randn(6, 4), torch.randn(4, 10), torch.randn(3, 3)]
+    lrs = [1e-3, 1e-3, 5e-4]
+    twins = [p.clone().requires_grad_(True) for p in ps]
+    opt = torch.optim.AdamW([{"params": twins[:2], "lr": 1e-3}, {"params": twins[2:], "lr": 5e-4}],
+                            betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    traj = []
+    for step in range(1, 5):
+        gs = [torch.randn_like(p) * (2.0 if step % 2 else 0.05) for p in ps]
+        for t, g in zip(twins, gs):
+            t.grad = g.clone()
+        total = torch.nn.utils.clip_grad_norm_(twins, 1.0)
+        opt.step()
+        traj.append(dict(grads=gs, total_norm=float(total), params=[t.detach().clone() for t in twins]))
+    torch.save(dict(p0=ps, lrs=lrs, traj=traj), f"{OUT}/adamw_clip.pt")
+
+
+if __name__ == "__main__":
+    R = load_ref_lora()
+    gen_ops(R)
+    gen_ctor_rng(R)
+    gen_inject(R)
+    gen_manifest(R)
+    gen_svd(R)
+    gen_adamw()
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(f"{OUT}/{fn}"))

@@ -1,0 +1,139 @@
+"""Pin the oracle (oracle/*.py) against golden vectors produced by RUNNING the real reference
+(/root/reference/lora_diffusion/lora.py, cli_svd.py; scripts/make_golden.py). CPU only.
+
+Tolerance: the reference ran in fp32 (torch eager CPU), the oracle in float64: 2e-5 relative."""
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import lora_ops as O
+from oracle import svd_ref
+from oracle.ref_modules import RefLoraSite
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def test_linear_forward_backward_vs_reference_golden():
+    cases = torch.load(f"{GOLD}/ops_linear.pt")
+    assert len(cases) >= 4
+    for c in cases:
+        x = c["x"]
+        M = x.shape[0] * x.shape[1]
+        x2, gy2 = x.reshape(M, -1), c["gy"].reshape(M, -1)
+        y = O.lora_linear_forward(x2, c["W"], c["b"], c["A"], c["B"], c["scale"], diag=c["diag"])
+        assert rel(y, c["y"].reshape(M, -1)) < 2e-5
+        dX, dA, dB = O.lora_linear_backward(gy2, x2, c["W"], c["A"], c["B"], c["scale"], diag=c["diag"])
+        assert rel(dX, c["dX"].reshape(M, -1)) < 2e-5
+        assert rel(dA, c["dA"]) < 2e-5
+        assert rel(dB, c["dB"]) < 2e-5
+
+
+def test_conv_forward_backward_vs_reference_golden():
+    cases = torch.load(f"{GOLD}/ops_conv.pt")
+    for c in cases:
+        y = O.lora_conv2d_forward(c["x"], c["W"], c["b"], c["A"], c["B"], c["scale"], padding=c["padding"])
+        assert rel(y, c["y"]) < 2e-5
+        dX, dA, dB = O.lora_conv2d_backward(c["gy"], c["x"], c["W"], c["A"], c["B"], c["scale"],
+                                            padding=c["padding"])
+        assert rel(dX, c["dX"]) < 2e-5
+        assert rel(dA, c["dA"]) < 2e-5
+        assert rel(dB, c["dB"]) < 2e-5
+
+
+def test_dropout_is_identity_in_eval_mode_golden():
+    c = torch.load(f"{GOLD}/ops_dropout_eval.pt")
+    y = O.lora_linear_forward(c["x"], c["W"], None, c["A"], c["B"], 1.0)
+    assert rel(y, c["y_eval"]) < 2e-5
+
+
+def test_dropout_mask_semantics():
+    """keep-mask m: branch * m / (1-p) (nn.Dropout, lora.py:45,56); gradients see the same mask."""
+    torch.manual_seed(0)
+    x, W, A, B = torch.randn(6, 8), torch.randn(5, 8), torch.randn(2, 8), torch.randn(5, 2)
+    mask = (torch.rand(6, 5) > 0.3).double()
+    y = O.lora_linear_forward(x, W, None, A, B, 0.5, keep_mask=mask, dropout_p=0.3)
+    base = x.double() @ W.double().T
+    assert torch.allclose(y - base, (x.double() @ A.double().T @ B.double().T) * mask / 0.7 * 0.5)
+    xa = x.clone().requires_grad_(True)
+    Aa, Ba = A.clone().double().requires_grad_(True), B.clone().double().requires_grad_(True)
+    ya = xa.double() @ W.double().T + ((xa.double() @ Aa.T) @ Ba.T) * mask / 0.7 * 0.5
+    gy = torch.randn(6, 5).double()
+    ya.backward(gy)
+    dX, dA, dB = O.lora_linear_backward(gy, x, W, A, B, 0.5, keep_mask=mask, dropout_p=0.3)
+    assert rel(dX, xa.grad) < 1e-6 and rel(dA, Aa.grad) < 1e-12 and rel(dB, Ba.grad) < 1e-12
+
+
+def test_ref_modules_match_reference_golden():
+    """oracle/ref_modules.RefLoraSite (torch eager restatement) == reference outputs and grads."""
+    for c in torch.load(f"{GOLD}/ops_linear.pt"):
+        N, K = c["W"].shape
+        base = nn.Linear(K, N, bias=c["b"] is not None)
+        base.weight.data.copy_(c["W"])
+        if c["b"] is not None:
+            base.bias.data.copy_(c["b"])
+        base.requires_grad_(False)
+        s = RefLoraSite(base, r=c["A"].shape[0], dropout_p=0.0, scale=c["scale"])
+        s.down.data.copy_(c["A"]); s.up.data.copy_(c["B"]); s.diag = c["diag"]
+        x = c["x"].clone().requires_grad_(True)
+        y = s(x)
+        y.backward(c["gy"])
+        assert rel(y, c["y"]) < 1e-6 and rel(x.grad, c["dX"]) < 1e-5
+        assert rel(s.down.grad, c["dA"]) < 1e-5 and rel(s.up.grad, c["dB"]) < 1e-5
+    for c in torch.load(f"{GOLD}/ops_conv.pt"):
+        Cout, Cin, k, _ = c["W"].shape
+        base = nn.Conv2d(Cin, Cout, k, 1, c["padding"], bias=c["b"] is not None)
+        base.weight.data.copy_(c["W"])
+        if c["b"] is not None:
+            base.bias.data.copy_(c["b"])
+        base.requires_grad_(False)
+        s = RefLoraSite(base, r=c["A"].shape[0], dropout_p=0.0, scale=c["scale"])
+        s.down.data.copy_(c["A"]); s.up.data.copy_(c["B"])
+        x = c["x"].clone().requires_grad_(True)
+        y = s(x)
+        y.backward(c["gy"])
+        assert rel(y, c["y"]) < 1e-6 and rel(x.grad, c["dX"]) < 1e-5
+        assert rel(s.down.grad, c["dA"]) < 1e-5 and rel(s.up.grad, c["dB"]) < 1e-5
+
+
+def test_clip_adamw_oracle_vs_torch_golden():
+    """torch.optim.AdamW + clip_grad_norm_ (the calls the reference makes) trajectory."""
+    d = torch.load(f"{GOLD}/adamw_clip.pt")
+    p = [x.clone() for x in d["p0"]]
+    m = [torch.zeros_like(x) for x in p]
+    v = [torch.zeros_like(x) for x in p]
+    for step, t in enumerate(d["traj"], start=1):
+        p, m, v, total = O.clip_adamw_step(p, t["grads"], m, v, step, d["lrs"])
+        assert abs(total - t["total_norm"]) < 1e-5 * t["total_norm"]
+        for a, b in zip(p, t["params"]):
+            assert rel(a, b) < 2e-6
+
+
+def test_clip_adamw_inv_world_equals_mean_of_rank_grads():
+    torch.manual_seed(1)
+    p = [torch.randn(5, 3)]
+    g0, g1 = torch.randn(5, 3), torch.randn(5, 3)
+    a = O.clip_adamw_step(p, [g0 + g1], [torch.zeros(5, 3)], [torch.zeros(5, 3)], 1, [1e-3], inv_world=0.5)
+    b = O.clip_adamw_step(p, [(g0 + g1) / 2], [torch.zeros(5, 3)], [torch.zeros(5, 3)], 1, [1e-3])
+    assert rel(a[0][0], b[0][0]) < 1e-14 and abs(a[3] - b[3]) < 1e-12
+
+
+def test_svd_oracle_vs_reference_golden():
+    """cli_svd.overwrite_base outputs. Same LAPACK here as when the golden was made, so factors
+    match elementwise up to fp32 noise; the sign-invariant quantities are checked as well."""
+    for c in torch.load(f"{GOLD}/svd_distill.pt"):
+        up, down, S, hi = svd_ref.svd_distill_pair(c["Wb"], c["Wt"], c["rank"], c["q"])
+        assert up.shape == c["up"].shape and down.shape == c["down"].shape
+        prod = up.flatten(1) @ down.flatten(1)
+        prod_ref = c["up"].flatten(1) @ c["down"].flatten(1)
+        assert rel(prod, prod_ref) < 1e-4
+        # clamp rule: nothing exceeds hi, and (same LAPACK build) the factors agree elementwise
+        assert float(max(up.abs().max(), down.abs().max())) <= hi * (1 + 1e-6)
+        assert float(max(c["up"].abs().max(), c["down"].abs().max())) <= hi * (1 + 1e-4)
+        assert rel(up, c["up"]) < 1e-3 and rel(down, c["down"]) < 1e-3
