@@ -41,7 +41,9 @@ int lb_abi_version(void);
 /* Fused frozen linear + LoRA forward (tcgen05/TMEM/TMA), one launch:
  *     Y[M,N] = X[M,K] . W[N,K]^T (+ bias[N]) + ((X . down16^T) * (scale * diag)) . up^T
  * up element (n, j) is read from the fp32 master at up[n*up_rs + j*up_cs]; diag is the optional
- * selector diagonal [r] (NULL = identity); T_out (NULL = skip) receives X . down16^T (unscaled).
+ * selector diagonal [r] (NULL = identity); T_out (NULL = skip) receives X . down16^T (unscaled);
+ * T_in (normally NULL): when given, the rank-r activations are read from this fp32 [M,16] buffer
+ * instead of being computed (dropout path: T = (mask o gY) . B comes from lb_lora_dropout_dt).
  * Replaces LoraInjectedLinear.forward, lora_diffusion/lora.py:53-58 (F.linear + lora_down +
  * selector + lora_up + scale + add), dropout handled by the caller.
  *
@@ -51,8 +53,8 @@ int lb_abi_version(void);
  */
 int lb_lora_linear_fwd(const void* X, const void* W, const float* bias, const void* down16,
                        const float* up, long long up_rs, long long up_cs, const float* diag,
-                       float scale, void* Y, float* T_out, int M, int K, int N, int r,
-                       int in_dtype, int out_dtype, void* stream);
+                       float scale, void* Y, float* T_out, const float* T_in, int M, int K, int N,
+                       int r, int in_dtype, int out_dtype, void* stream);
 
 /* Skinny weight-gradient reduction (streams S once, fp32 atomics into out):
  *     out[j*out_js + c*out_cs] += scale * diag[j] * sum_m V[m,j] * S[m,c]     j < r, c < C
@@ -63,6 +65,62 @@ int lb_lora_linear_fwd(const void* X, const void* W, const float* bias, const vo
 int lb_lora_wgrad(const void* S, const float* V, const float* diag, float scale, float* out,
                   long long out_js, long long out_cs, int M, int C, int r, int in_dtype,
                   void* stream);
+
+/* Conv tap of the same reduction: rows of S are the pixels of NHWC images [M/(H*W), H, W, C]; S is
+ * read at pixel (h+dy, w+dx), zero outside the image (the convolution's zero padding):
+ *     out[...] += scale * diag[j] * sum_p V[p,j] * S[p shifted by (dy,dx), c]
+ * dA[r,Cin,kh,kw] of a LoraInjectedConv2d: one call per tap t = (ty,tx) with dy = ty - pad_h,
+ * dx = tx - pad_w, out = dA + t, out_js = Cin*kh*kw, out_cs = kh*kw, V = gY.B (per pixel).
+ * H = W = 0 degenerates to lb_lora_wgrad. Replaces the lora_down wgrad of lora.py:130-135. */
+int lb_lora_wgrad_shift(const void* S, const float* V, const float* diag, float scale, float* out,
+                        long long out_js, long long out_cs, int M, int C, int r, int H, int W,
+                        int dy, int dx, int in_dtype, void* stream);
+
+/* ---- dropout on the LoRA branch (nn.Dropout inside the operator, lora.py:45,56,115,133; active
+ * only when module.training and p > 0). keep(m,n) is a counter-based hash of (*seed_dev, m*N+n),
+ * recomputed by every kernel; seed_dev is a DEVICE uint64 so CUDA-graph replays draw new masks.
+ * Forward:  Y = lb_lora_linear_fwd(scale = 0)  ->  lb_lora_up_dropout adds the masked branch.
+ * Backward: dTs = lb_lora_dropout_dt(gY) -> lb_lora_linear_fwd(T_in = dTs) for dX ->
+ *           lb_lora_wgrad(X, dTs) for dA, lb_lora_wgrad_masked(gY, T) for dB. */
+/* Y[m,n] += scale/(1-p) * keep(m,n) * sum_j T[m,j]*diag[j]*up[n*up_rs + j*up_cs]   (in place) */
+int lb_lora_up_dropout(void* Y, int y_dtype, const float* T, const float* up, long long up_rs,
+                       long long up_cs, const float* diag, float scale, float drop_p,
+                       const void* seed_dev, int M, int N, int r, void* stream);
+/* dTs[m,j] = sum_n keep(m,n)/(1-p) * gY[m,n] * up[n*up_rs + j*up_cs]    (fp32 [M,16]) */
+int lb_lora_dropout_dt(const void* gY, int in_dtype, const float* up, long long up_rs,
+                       long long up_cs, float drop_p, const void* seed_dev, float* dTs, int M, int N,
+                       int r, void* stream);
+/* lb_lora_wgrad with S := keep o S / (1-p)  (S = gY [M,C], mask index m*C + c) */
+int lb_lora_wgrad_masked(const void* S, const float* V, const float* diag, float scale, float* out,
+                         long long out_js, long long out_cs, int M, int C, int r, float drop_p,
+                         const void* seed_dev, int in_dtype, void* stream);
+
+/* Fused frozen Conv2d + LoRA (NHWC implicit GEMM on tcgen05; stride 1, dilation 1, groups 1,
+ * 1x1 or 3x3 "same" padding -- the ResnetBlock2D sites of SD1.5):
+ *     Y[n,h,w,:] = sum_tap X[n,h+ty-pad,w+tx-pad,:] . W[:, tap, :]^T (+ bias)
+ *                  + ((sum_tap X[..] . down16[:, tap, :]^T) * (scale*diag)) . up^T
+ * X: NHWC 16-bit [n_img,H,W,Cin]; W: 16-bit [Cout, kh*kw*Cin] with K ordered tap-major,
+ * channel-minor (built once from the frozen [Cout,Cin,kh,kw] weight); down16: [16, kh*kw*Cin] in
+ * the same K order; up element (n, j) at up[n*up_rs + j*up_cs]; Y: NHWC [n_img,H,W,Cout];
+ * T_out: fp32 [n_img*H*W, 16] = the rank-r activations (unscaled).
+ * Replaces LoraInjectedConv2d.forward, lora_diffusion/lora.py:130-135.
+ *
+ * per_tap_T = 1 is the input-gradient form (dX = conv_T(gY, W) + conv_T((gY.B)*s*d, A)): call it
+ * with X := gY [n_img,H,W,Cout'], W := the flipped+transposed frozen weight [Cin', taps*Cout'],
+ * down16 := B^T padded [16, Cout'] (restarts every tap), up := A read flipped:
+ * element (c, tap g, j) at up[c*up_rs + j*up_cs + g*up_gs] (up_gs = -1 from the last tap).
+ * T_out then receives gY.B of the unshifted tap. */
+int lb_lora_conv2d_fwd(const void* X, const void* W, const float* bias, const void* down16,
+                       const float* up, long long up_rs, long long up_cs, long long up_gs,
+                       const float* diag, float scale, void* Y, float* T_out, const float* T_in,
+                       int n_img, int H, int Wd, int Cin, int Cout, int kh, int kw, int pad_h,
+                       int pad_w, int r, int per_tap_T, int in_dtype, int out_dtype, void* stream);
+
+/* Frozen conv-weight preparation: src [Cout,Cin,kh,kw] (LB_F32/LB_BF16/LB_F16) ->
+ *   dst16  [Cout, kh*kw*Cin]  (tap-major K; forward operand)              and/or
+ *   dstT16 [Cin, kh*kw*Cout]  with taps flipped (input-gradient operand). Either may be NULL. */
+int lb_cast_conv_weight(const void* src, int src_dtype, void* dst16, void* dstT16, int Cout,
+                        int Cin, int kh, int kw, int out_dtype, void* stream);
 
 /* dst16[j, c] = (j < r) ? src[j*src_rs + c*src_cs] : 0   for j < 16, c < C  (16-bit, [16,C]).
  * A[r,K] -> down16:  src_rs = K, src_cs = 1.    B[N,r] -> B^T padded: src_rs = 1, src_cs = r. */

@@ -31,7 +31,7 @@ def _load():
     vp, ll, i32, f32 = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float
     sig = {
         "lb_abi_version": ([], i32),
-        "lb_lora_linear_fwd": ([vp, vp, vp, vp, vp, ll, ll, vp, f32, vp, vp,
+        "lb_lora_linear_fwd": ([vp, vp, vp, vp, vp, ll, ll, vp, f32, vp, vp, vp,
                                 i32, i32, i32, i32, i32, i32, vp], i32),
         "lb_lora_wgrad": ([vp, vp, vp, f32, vp, ll, ll, i32, i32, i32, i32, vp], i32),
         "lb_cast_rows_pad16": ([vp, ll, ll, vp, i32, i32, i32, vp], i32),
@@ -39,9 +39,15 @@ def _load():
         "lb_adamw_clip_step": ([vp, vp, vp, vp, ll, ctypes.POINTER(ll), i32, vp, f32, f32, f32,
                                 f32, f32, f32, vp, vp, vp, vp], i32),
         "lb_refresh_shadows": ([vp, vp, i32, i32, vp, i32, vp], i32),
-        "lb_lora_conv2d_fwd": ([vp, vp, vp, vp, vp, ll, ll, vp, f32, vp, vp,
-                                i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
-        "lb_svd_lowrank": None,
+        "lb_lora_wgrad_shift": ([vp, vp, vp, f32, vp, ll, ll, i32, i32, i32, i32, i32, i32, i32,
+                                 i32, vp], i32),
+        "lb_lora_conv2d_fwd": ([vp, vp, vp, vp, vp, ll, ll, ll, vp, f32, vp, vp, vp,
+                                i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32,
+                                vp], i32),
+        "lb_cast_conv_weight": ([vp, i32, vp, vp, i32, i32, i32, i32, i32, vp], i32),
+        "lb_lora_up_dropout": ([vp, i32, vp, vp, ll, ll, vp, f32, f32, vp, i32, i32, i32, vp], i32),
+        "lb_lora_dropout_dt": ([vp, i32, vp, ll, ll, f32, vp, vp, i32, i32, i32, vp], i32),
+        "lb_lora_wgrad_masked": ([vp, vp, vp, f32, vp, ll, ll, i32, i32, i32, f32, vp, i32, vp], i32),
     }
     for name, s in sig.items():
         if s is None or not hasattr(lib, name):
@@ -54,7 +60,9 @@ def _load():
 lib = _load()
 EXPORTED = [n for n in ("lb_abi_version", "lb_lora_linear_fwd", "lb_lora_wgrad",
                         "lb_cast_rows_pad16", "lb_cast_weight", "lb_adamw_clip_step",
-                        "lb_refresh_shadows")]
+                        "lb_refresh_shadows", "lb_lora_wgrad_shift", "lb_lora_conv2d_fwd",
+                        "lb_cast_conv_weight", "lb_lora_up_dropout", "lb_lora_dropout_dt",
+                        "lb_lora_wgrad_masked")]
 
 
 def check(status: int, what: str):

@@ -1,0 +1,357 @@
+// Fused frozen-weight GEMM / implicit-GEMM conv + rank-r LoRA for sm_100a (tcgen05 + TMEM + TMA).
+//
+//   Y[M,N] = X[M,K] . W[N,K]^T (+ bias) + sum_g ((X_g . D^T) * (scale * diag)) . U_g^T
+//
+// LINEAR  (CONV = false):  X is a row-major [M,K] matrix, one T group (G = 1).
+// CONV    (CONV = true):   X is an NHWC activation; a CTA owns a TH x TW pixel rectangle
+//                          (TH*TW = 128 rows) and walks K = (filter tap, 64-channel block); each
+//                          tap is the same rectangle shifted by (dy - pad, dx - pad), fetched by a
+//                          4-D TMA box whose out-of-image part is zero-filled by the hardware
+//                          (that IS the padding). Stride 1, dilation 1, groups 1.
+//
+// The LoRA down factor D ([16, K] 16-bit, zero-padded rank) rides the main K loop: its 16 rows are
+// appended below every W tile in shared memory, so the tensor core produces T = X.D^T alongside
+// the base accumulator from the same X tile -- X is read from HBM exactly once.
+//   G == 1: one tcgen05.mma per K-step with N = BLOCK_N + 16; T lives in TMEM columns
+//           [BLOCK_N, BLOCK_N+16).                       (linear fwd / dX, conv fwd, 1x1 conv dX)
+//   G  > 1: the conv input-gradient. dX needs a separate T_t = gY(shifted by tap t) . B per tap,
+//           so each K-step issues N = BLOCK_N into the accumulator and N = 16 into the tap's own
+//           TMEM columns [BLOCK_N + 16 t, +16).
+// After the K loop the epilogue warps pull the T group(s) out of TMEM, scale them, write them back
+// to shared memory as 16-bit K-major operands, and the MMA warp accumulates
+// acc += T'_g . U_g^T (K = 16 each) into the same TMEM accumulator. Bias is added in the epilogue
+// and the tile leaves through a swizzled staging buffer and TMA stores.
+#pragma once
+#include "ptx.cuh"
+
+namespace lb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 x 16-bit = 128 B = one SWIZZLE_128B row
+constexpr int R_PAD = 16;    // LoRA rank padded to one UMMA K-step
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;  // warp0 TMA, warp1 MMA + TMEM alloc, warps2-5 epilogue
+constexpr int EPI_THREADS = 128;
+
+struct FusedParams {
+  const float* bias;   // [N] or null
+  const float* up;     // fp32 LoRA-up factor: element (n, g, j) at up[n*up_rs + j*up_cs + g*up_gs]
+  long long up_rs, up_cs, up_gs;
+  const float* diag;   // [r] or null (selector diagonal)
+  float* t_out;        // [M,16] fp32 side output (group t_group, unscaled), n_blk == 0 CTAs; or null
+  const float* t_in;   // [M,16] fp32 or null: when set, the rank-r activations are TAKEN from here
+                       // (row = this row / the tap-shifted pixel) instead of from TMEM. Used by the
+                       // dropout path, where T = (mask o gY).B cannot share the base operand.
+  float scale;
+  int M, N, K, r;      // K = total reduction length (conv: taps * C)
+  int fmt;             // 1 = bf16 operands, 0 = fp16
+  int t_group;         // which T group goes to t_out
+  // conv geometry
+  int H, W, C;         // image height/width, input channels
+  int kh, kw, pad_h, pad_w;
+  int TH, TW, tiles_h, tiles_w;
+  int down_per_tap;    // 1: D columns advance with the tap (forward); 0: D restarts every tap (dX)
+};
+
+template <int BLOCK_N, int STAGES, typename OutT, int G>
+struct Smem {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = (BLOCK_N + R_PAD) * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BOX_COLS = 128 / sizeof(OutT);  // columns per 128-byte store box
+  static constexpr int NUM_BOXES = BLOCK_N / BOX_COLS;
+  static constexpr int BOX_BYTES = BLOCK_M * 128;
+  static constexpr int T_BYTES = BLOCK_M * R_PAD * G * 2;   // T' operand(s)
+  static constexpr int UP_BYTES = BLOCK_N * R_PAD * G * 2;  // U tile(s)
+  static constexpr int OFF_EPI = STAGES * STAGE_BYTES;
+  // output staging is written only after the last MMA has consumed T'/U: the regions alias
+  static constexpr int OFF_OUT = OFF_EPI;
+  static constexpr int OFF_T = OFF_EPI;
+  static constexpr int OFF_UP = OFF_T + T_BYTES;
+  static constexpr int EPI_BYTES =
+      (NUM_BOXES * BOX_BYTES > T_BYTES + UP_BYTES) ? NUM_BOXES * BOX_BYTES : T_BYTES + UP_BYTES;
+  static constexpr int OFF_BIAS = OFF_EPI + ((EPI_BYTES + 1023) / 1024) * 1024;
+  static constexpr int OFF_BAR = OFF_BIAS + BLOCK_N * 4;
+  static constexpr int NUM_BARS = 2 * STAGES + 3;
+  static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+  static constexpr int TOTAL = OFF_TMEM + 16;
+  static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
+  static constexpr int ACC_COLS = BLOCK_N + R_PAD * G;
+  static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);
+  static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
+  static_assert(ACC_COLS <= 512, "TMEM budget exceeded");
+};
+
+template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY,
+                  const FusedParams p) {
+  using S = Smem<BLOCK_N, STAGES, OutT, G>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));  // generic pointer to the aligned base
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x, m_blk = blockIdx.y;
+  const int n0 = n_blk * BLOCK_N;
+  // row-tile origin
+  int m0 = m_blk * BLOCK_M;   // LINEAR: first row
+  int img = 0, h0 = 0, w0 = 0;  // CONV: image index and rectangle origin
+  if constexpr (CONV) {
+    const int per_img = p.tiles_h * p.tiles_w;
+    img = m_blk / per_img;
+    const int rem = m_blk - img * per_img;
+    h0 = (rem / p.tiles_w) * p.TH;
+    w0 = (rem % p.tiles_w) * p.TW;
+  }
+  const int taps = CONV ? p.kh * p.kw : 1;
+  const int cblocks = CONV ? (p.C + BLOCK_K - 1) / BLOCK_K : (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_kb = taps * cblocks;
+
+  auto bar_full = [&](int s) { return sbase + S::OFF_BAR + 8 * s; };
+  auto bar_empty = [&](int s) { return sbase + S::OFF_BAR + 8 * (STAGES + s); };
+  const uint32_t bar_acc = sbase + S::OFF_BAR + 8 * (2 * STAGES + 0);     // K loop finished
+  const uint32_t bar_tready = sbase + S::OFF_BAR + 8 * (2 * STAGES + 1);  // T' operand(s) in smem
+  const uint32_t bar_final = sbase + S::OFF_BAR + 8 * (2 * STAGES + 2);   // LoRA MMAs finished
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + S::OFF_TMEM);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    tma_prefetch_desc(&tmD);
+    tma_prefetch_desc(&tmY);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_empty(s), 1);
+    }
+    mbar_init(bar_acc, 1);
+    mbar_init(bar_tready, EPI_THREADS);
+    mbar_init(bar_final, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(sbase + S::OFF_TMEM, S::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_empty(s), ph ^ 1);
+        mbar_expect_tx(bar_full(s), S::STAGE_BYTES);
+        const uint32_t sa = sbase + s * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+        if constexpr (CONV) {
+          const int tap = kb / cblocks, cb = kb - tap * cblocks;
+          const int dy = tap / p.kw, dx = tap - dy * p.kw;
+          tma_load_4d(&tmX, bar_full(s), sa, cb * BLOCK_K, w0 + dx - p.pad_w, h0 + dy - p.pad_h, img);
+          tma_load_2d(&tmW, bar_full(s), sb, tap * p.C + cb * BLOCK_K, n0);
+          tma_load_2d(&tmD, bar_full(s), sb + BLOCK_N * 128,
+                      (p.down_per_tap ? tap * p.C : 0) + cb * BLOCK_K, 0);
+        } else {
+          tma_load_2d(&tmX, bar_full(s), sa, kb * BLOCK_K, m0);
+          tma_load_2d(&tmW, bar_full(s), sb, kb * BLOCK_K, n0);
+          tma_load_2d(&tmD, bar_full(s), sb + BLOCK_N * 128, kb * BLOCK_K, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      const uint32_t idesc_wide = umma_idesc_f16(p.fmt, BLOCK_M, BLOCK_N + R_PAD);
+      const uint32_t idesc_base = umma_idesc_f16(p.fmt, BLOCK_M, BLOCK_N);
+      const uint32_t idesc_t = umma_idesc_f16(p.fmt, BLOCK_M, R_PAD);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(bar_full(s), ph);
+        tc_fence_after();
+        const uint32_t sa = sbase + s * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+        const int tap = (G > 1) ? kb / cblocks : 0;
+        const bool tap_first = (G > 1) ? (kb - tap * cblocks) == 0 : false;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // K-major SWIZZLE_128B: 8-row groups 1024 B apart; one K-step = 32 B along the row
+          const uint64_t ad = umma_smem_desc(sa + k * UMMA_K * 2, 16, 1024, 2);
+          const uint64_t bd = umma_smem_desc(sb + k * UMMA_K * 2, 16, 1024, 2);
+          if constexpr (G == 1) {
+            umma_f16_ss(tmem, ad, bd, idesc_wide, (kb | k) != 0);
+          } else {
+            const uint64_t dd = umma_smem_desc(sb + BLOCK_N * 128 + k * UMMA_K * 2, 16, 1024, 2);
+            umma_f16_ss(tmem, ad, bd, idesc_base, (kb | k) != 0);
+            umma_f16_ss(tmem + BLOCK_N + R_PAD * tap, ad, dd, idesc_t, !(tap_first && k == 0));
+          }
+        }
+        umma_commit(bar_empty(s));  // frees the smem slot when these MMAs retire
+      }
+      umma_commit(bar_acc);
+      // LoRA up-projection(s): acc[:, 0:BLOCK_N] += T'_g[128,16] . U_g[BLOCK_N,16]^T
+      mbar_wait(bar_tready, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        // no-swizzle K-major operand of total K = 16 G: core matrix = 8 rows x 16 B (128 B
+        // contiguous); LBO = 128 B (next K core matrix), SBO = 256 G bytes (next 8-row group)
+        const uint64_t ad = umma_smem_desc(sbase + S::OFF_T + g * 256, 128, 256 * G, 0);
+        const uint64_t bd = umma_smem_desc(sbase + S::OFF_UP + g * 256, 128, 256 * G, 0);
+        umma_f16_ss(tmem, ad, bd, idesc_base, 1);
+      }
+      umma_commit(bar_final);
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps (128 threads)
+    const int q = warp & 3;         // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;  // accumulator row owned by this thread
+    const int et = threadIdx.x - 64;
+    float* bias_s = reinterpret_cast<float*>(sgen + S::OFF_BIAS);
+
+    // Stage the U tile(s) (fp32 master -> 16-bit, interleaved core-matrix layout) and the bias.
+    for (int i = et; i < BLOCK_N; i += EPI_THREADS) {
+      const int n = n0 + i;
+      const bool ok = n < p.N;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float u[R_PAD];
+#pragma unroll
+        for (int j = 0; j < R_PAD; ++j)
+          u[j] = (ok && j < p.r) ? __ldg(p.up + n * p.up_rs + j * p.up_cs + g * p.up_gs) : 0.f;
+        const uint32_t dst = sbase + S::OFF_UP + (i >> 3) * (256 * G) + g * 256 + (i & 7) * 16;
+        st_shared_v4(dst, pack2(u[0], u[1], p.fmt), pack2(u[2], u[3], p.fmt),
+                     pack2(u[4], u[5], p.fmt), pack2(u[6], u[7], p.fmt));
+        st_shared_v4(dst + 128, pack2(u[8], u[9], p.fmt), pack2(u[10], u[11], p.fmt),
+                     pack2(u[12], u[13], p.fmt), pack2(u[14], u[15], p.fmt));
+      }
+      bias_s[i] = (p.bias != nullptr && ok) ? __ldg(p.bias + n) : 0.f;
+    }
+    float coef[R_PAD];
+#pragma unroll
+    for (int j = 0; j < R_PAD; ++j)
+      coef[j] = (j < p.r) ? p.scale * (p.diag ? __ldg(p.diag + j) : 1.f) : 0.f;
+
+    // global row (pixel) this thread owns, for the T side output
+    long long grow = -1;
+    if constexpr (CONV) {
+      const int hh = h0 + row / p.TW, ww = w0 + row % p.TW;
+      if (hh < p.H && ww < p.W) grow = (static_cast<long long>(img) * p.H + hh) * p.W + ww;
+    } else {
+      if (m0 + row < p.M) grow = m0 + row;
+    }
+
+    // T group(s) out of TMEM -> (optional) global save -> scaled 16-bit operand(s) in smem
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float t[R_PAD];
+      if (p.t_in == nullptr) {
+        uint32_t tv[R_PAD];
+        tmem_ld16(tmem + (static_cast<uint32_t>(q * 32) << 16) + BLOCK_N + R_PAD * g, tv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < R_PAD; ++j) t[j] = __uint_as_float(tv[j]);
+      } else {
+        long long srow = grow;
+        if constexpr (CONV && G > 1) {   // group g = tap g: the pixel shifted by (dy - pad, dx - pad)
+          const int hh = h0 + row / p.TW + g / p.kw - p.pad_h;
+          const int ww = w0 + row % p.TW + g % p.kw - p.pad_w;
+          srow = (grow >= 0 && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W)
+                     ? (static_cast<long long>(img) * p.H + hh) * p.W + ww : -1;
+        }
+        if (srow >= 0) {
+          const float4* src = reinterpret_cast<const float4*>(p.t_in + srow * R_PAD);
+          const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2), d = __ldg(src + 3);
+          t[0] = a.x; t[1] = a.y; t[2] = a.z; t[3] = a.w; t[4] = b.x; t[5] = b.y; t[6] = b.z; t[7] = b.w;
+          t[8] = c.x; t[9] = c.y; t[10] = c.z; t[11] = c.w; t[12] = d.x; t[13] = d.y; t[14] = d.z; t[15] = d.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < R_PAD; ++j) t[j] = 0.f;
+        }
+      }
+      if (p.t_out != nullptr && n_blk == 0 && g == p.t_group && grow >= 0) {
+        float4* dst = reinterpret_cast<float4*>(p.t_out + grow * R_PAD);
+        dst[0] = make_float4(t[0], t[1], t[2], t[3]);
+        dst[1] = make_float4(t[4], t[5], t[6], t[7]);
+        dst[2] = make_float4(t[8], t[9], t[10], t[11]);
+        dst[3] = make_float4(t[12], t[13], t[14], t[15]);
+      }
+#pragma unroll
+      for (int j = 0; j < R_PAD; ++j) t[j] *= coef[j];
+      const uint32_t dst = sbase + S::OFF_T + (row >> 3) * (256 * G) + g * 256 + (row & 7) * 16;
+      st_shared_v4(dst, pack2(t[0], t[1], p.fmt), pack2(t[2], t[3], p.fmt),
+                   pack2(t[4], t[5], p.fmt), pack2(t[6], t[7], p.fmt));
+      st_shared_v4(dst + 128, pack2(t[8], t[9], p.fmt), pack2(t[10], t[11], p.fmt),
+                   pack2(t[12], t[13], p.fmt), pack2(t[14], t[15], p.fmt));
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor-core proxy
+    mbar_arrive(bar_tready);
+    named_bar_sync(1, EPI_THREADS);  // bias_s complete for every epilogue thread
+
+    // Final accumulator -> (+bias) -> OutT -> swizzled staging -> TMA store
+    mbar_wait(bar_final, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_s[c * 32 + j];
+      if constexpr (sizeof(OutT) == 2) {
+        const int box = c >> 1;
+        const uint32_t rbase = sbase + S::OFF_OUT + box * S::BOX_BYTES + row * 128;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const int piece = ((c & 1) * 4 + qq) ^ (row & 7);
+          st_shared_v4(rbase + piece * 16, pack2(f[qq * 8 + 0], f[qq * 8 + 1], p.fmt),
+                       pack2(f[qq * 8 + 2], f[qq * 8 + 3], p.fmt),
+                       pack2(f[qq * 8 + 4], f[qq * 8 + 5], p.fmt),
+                       pack2(f[qq * 8 + 6], f[qq * 8 + 7], p.fmt));
+        }
+      } else {
+        const uint32_t rbase = sbase + S::OFF_OUT + c * S::BOX_BYTES + row * 128;
+#pragma unroll
+        for (int qq = 0; qq < 8; ++qq) {
+          const int piece = qq ^ (row & 7);
+          st_shared_v4(rbase + piece * 16, __float_as_uint(f[qq * 4 + 0]),
+                       __float_as_uint(f[qq * 4 + 1]), __float_as_uint(f[qq * 4 + 2]),
+                       __float_as_uint(f[qq * 4 + 3]));
+        }
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async_smem();
+    named_bar_sync(1, EPI_THREADS);
+    if (et == 0) {
+      for (int b = 0; b < S::NUM_BOXES; ++b) {
+        const int col = n0 + b * S::BOX_COLS;
+        if (col >= p.N) break;
+        if constexpr (CONV)
+          tma_store_4d(&tmY, sbase + S::OFF_OUT + b * S::BOX_BYTES, col, w0, h0, img);
+        else
+          tma_store_2d(&tmY, sbase + S::OFF_OUT + b * S::BOX_BYTES, col, m0);
+      }
+      tma_store_commit();
+      tma_store_wait_read0();
+    }
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, S::TMEM_COLS);
+  }
+}
+
+}  // namespace lb

@@ -32,6 +32,19 @@ __device__ __forceinline__ float from16(uint16_t x, int fmt) {
   return __half2float(*reinterpret_cast<__half*>(&x));
 }
 
+// ------------------------------------------------------------------------------- dropout mask
+// Counter-based keep decision for element `idx` of the LoRA-branch output (nn.Dropout,
+// lora.py:45,56): a splitmix64 finaliser of (seed + idx * golden). Forward and the three backward
+// kernels recompute the same bit from (seed, idx); nothing is stored. The stream differs from
+// ATen's Philox, so parity with the reference under dropout is statistical.
+__device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long idx, float p) {
+  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return static_cast<float>(z >> 40) * (1.0f / 16777216.0f) >= p;
+}
+
 // ------------------------------------------------------------------------------- wgrad
 // CTA = 8 warps over a [ROWS x 64-column] slab of S. Lane owns 2 adjacent columns (one 32-bit
 // load; a warp reads one full 128-B line per row). Warps stride over rows. Each thread keeps
@@ -44,7 +57,8 @@ template <int RQ>  // number of float4 groups of V actually used: ceil(r/4)
 __global__ void __launch_bounds__(WG_WARPS * 32)
 wgrad_kernel(const uint32_t* __restrict__ S, const float* __restrict__ V,
              const float* __restrict__ diag, float scale, float* __restrict__ out,
-             long long out_js, long long out_cs, int M, int C, int r, int fmt) {
+             long long out_js, long long out_cs, int M, int C, int r, int fmt, int cH, int cW,
+             int dy, int dx, float drop_p, const unsigned long long* __restrict__ seed_dev) {
   __shared__ float red[WG_WARPS][RQ * 4][WG_COLS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = blockIdx.x * WG_COLS + lane * 2;
@@ -58,8 +72,24 @@ wgrad_kernel(const uint32_t* __restrict__ S, const float* __restrict__ V,
   for (int j = 0; j < RQ * 4; ++j) acc[j][0] = acc[j][1] = 0.f;
 
   for (int m = m_begin + warp; m < m_end; m += WG_WARPS) {
-    const uint32_t w = col_ok ? __ldg(S + static_cast<size_t>(m) * pitch + (c0 >> 1)) : 0u;
-    const float2 x = ld16x2(w, fmt);
+    // conv weight-gradient taps: row m is pixel (h, w) of an NHWC image; S is read at the pixel
+    // shifted by (dy, dx), zero outside the image (= the convolution's padding)
+    long long src = m;
+    bool ok = col_ok;
+    if (cH > 0) {
+      const int ww = m % cW + dx, hh = (m / cW) % cH + dy;
+      ok = ok && hh >= 0 && hh < cH && ww >= 0 && ww < cW;
+      src = static_cast<long long>(m) + dy * cW + dx;
+    }
+    const uint32_t w = ok ? __ldg(S + static_cast<size_t>(src) * pitch + (c0 >> 1)) : 0u;
+    float2 x = ld16x2(w, fmt);
+    if (drop_p > 0.f) {  // S = gY of a dropout site: the branch saw mask/(1-p)
+      const unsigned long long sd = seed_dev[0];
+      const unsigned long long e = static_cast<unsigned long long>(m) * C + c0;
+      const float inv = 1.f / (1.f - drop_p);
+      x.x = drop_keep(sd, e, drop_p) ? x.x * inv : 0.f;
+      x.y = drop_keep(sd, e + 1, drop_p) ? x.y * inv : 0.f;
+    }
     const float4* vrow = reinterpret_cast<const float4*>(V + static_cast<size_t>(m) * 16);
 #pragma unroll
     for (int qd = 0; qd < RQ; ++qd) {
@@ -86,6 +116,82 @@ wgrad_kernel(const uint32_t* __restrict__ S, const float* __restrict__ V,
       const float coef = scale * (diag ? diag[j] : 1.f);
       atomicAdd(out + j * out_js + cg * out_cs, coef * s);
     }
+  }
+}
+
+// ------------------------------------------------------------------------------- dropout branch
+// Y[m, n] += scale/(1-p) * keep(m,n) * sum_j (T[m,j] * diag[j]) * up[n, j]     (in place)
+// one thread = 8 consecutive columns of one row (16-byte access for 16-bit Y)
+template <typename YT>
+__global__ void __launch_bounds__(256)
+up_dropout_kernel(YT* __restrict__ Y, int y_fmt, const float* __restrict__ T,
+                  const float* __restrict__ up, long long up_rs, long long up_cs,
+                  const float* __restrict__ diag, float scale, float drop_p,
+                  const unsigned long long* __restrict__ seed_dev, int M, int N, int r) {
+  const int groups = N >> 3;  // N % 8 == 0
+  const long long gid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (gid >= static_cast<long long>(M) * groups) return;
+  const int m = static_cast<int>(gid / groups);
+  const int n0 = static_cast<int>(gid % groups) << 3;
+  const unsigned long long sd = seed_dev[0];
+  const float inv = scale / (1.f - drop_p);
+  float t[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) t[j] = (j < r) ? T[static_cast<size_t>(m) * 16 + j] * (diag ? diag[j] : 1.f) : 0.f;
+  float add[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float u = 0.f;
+    for (int j = 0; j < r; ++j) u += t[j] * __ldg(up + (n0 + i) * up_rs + j * up_cs);
+    add[i] = drop_keep(sd, static_cast<unsigned long long>(m) * N + n0 + i, drop_p) ? u * inv : 0.f;
+  }
+  YT* yp = Y + static_cast<size_t>(m) * N + n0;
+  if constexpr (sizeof(YT) == 2) {
+    uint4 raw = *reinterpret_cast<uint4*>(yp);
+    uint16_t* h = reinterpret_cast<uint16_t*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = to16(from16(h[i], y_fmt) + add[i], y_fmt);
+    *reinterpret_cast<uint4*>(yp) = raw;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) yp[i] += add[i];
+  }
+}
+
+// dTs[m, j] = sum_n keep(m,n)/(1-p) * gY[m,n] * up[n, j]     (one warp per row)
+__global__ void __launch_bounds__(256)
+dropout_dt_kernel(const uint32_t* __restrict__ gY, int fmt, const float* __restrict__ up,
+                  long long up_rs, long long up_cs, float drop_p,
+                  const unsigned long long* __restrict__ seed_dev, float* __restrict__ dTs, int M,
+                  int N, int r) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= M) return;
+  const int m = warp;
+  const unsigned long long sd = seed_dev[0];
+  const float inv = 1.f / (1.f - drop_p);
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  const size_t pitch = static_cast<size_t>(N) >> 1;
+  for (int n = lane * 2; n < N; n += 64) {
+    float2 g = ld16x2(__ldg(gY + static_cast<size_t>(m) * pitch + (n >> 1)), fmt);
+    const unsigned long long e = static_cast<unsigned long long>(m) * N + n;
+    g.x = drop_keep(sd, e, drop_p) ? g.x * inv : 0.f;
+    g.y = drop_keep(sd, e + 1, drop_p) ? g.y * inv : 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < r) acc[j] += g.x * __ldg(up + n * up_rs + j * up_cs) + g.y * __ldg(up + (n + 1) * up_rs + j * up_cs);
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+  if (lane == 0) {
+    float4* dst = reinterpret_cast<float4*>(dTs + static_cast<size_t>(m) * 16);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    dst[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
+    dst[3] = make_float4(acc[12], acc[13], acc[14], acc[15]);
   }
 }
 
@@ -140,6 +246,26 @@ __global__ void cast_weight_kernel(const SrcT* __restrict__ src, int src_fmt,
       if (rr < R && cc < C) dstT[static_cast<size_t>(cc) * R + rr] = to16(tile[threadIdx.x][i], fmt);
     }
   }
+}
+
+// frozen conv weight [Cout,Cin,T] -> forward operand [Cout, T*Cin] and flipped-transposed
+// input-gradient operand [Cin, T*Cout]; one-time per frozen weight, one thread per element
+template <typename SrcT>
+__global__ void cast_conv_weight_kernel(const SrcT* __restrict__ src, int src_fmt,
+                                        uint16_t* __restrict__ dst, uint16_t* __restrict__ dstT,
+                                        int Cout, int Cin, int T, int fmt) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(Cout) * Cin * T;
+  if (i >= total) return;
+  const int t = static_cast<int>(i % T);
+  const int c = static_cast<int>((i / T) % Cin);
+  const int o = static_cast<int>(i / (static_cast<long long>(T) * Cin));
+  float x;
+  if constexpr (sizeof(SrcT) == 4) x = src[i];
+  else x = from16(src[i], src_fmt);
+  const uint16_t v = to16(x, fmt);
+  if (dst) dst[(static_cast<long long>(o) * T + t) * Cin + c] = v;
+  if (dstT) dstT[(static_cast<long long>(c) * T + (T - 1 - t)) * Cout + o] = v;
 }
 
 // ------------------------------------------------------------------------------- clip + AdamW
@@ -243,9 +369,47 @@ using namespace lb;
 
 extern "C" int lb_abi_version(void) { return 1; }
 
+extern "C" int lb_lora_wgrad_shift(const void* S, const float* V, const float* diag, float scale,
+                                   float* out, long long out_js, long long out_cs, int M, int C,
+                                   int r, int H, int W, int dy, int dx, int in_dtype, void* stream);
+extern "C" int lb_lora_wgrad_masked(const void* S, const float* V, const float* diag, float scale,
+                                    float* out, long long out_js, long long out_cs, int M, int C,
+                                    int r, float drop_p, const void* seed_dev, int in_dtype,
+                                    void* stream);
+static int wgrad_launch(const void* S, const float* V, const float* diag, float scale, float* out,
+                        long long out_js, long long out_cs, int M, int C, int r, int H, int W,
+                        int dy, int dx, float drop_p, const void* seed_dev, int in_dtype,
+                        void* stream);
+
 extern "C" int lb_lora_wgrad(const void* S, const float* V, const float* diag, float scale,
                              float* out, long long out_js, long long out_cs, int M, int C, int r,
                              int in_dtype, void* stream) {
+  return lb_lora_wgrad_shift(S, V, diag, scale, out, out_js, out_cs, M, C, r, 0, 0, 0, 0, in_dtype,
+                             stream);
+}
+
+extern "C" int lb_lora_wgrad_shift(const void* S, const float* V, const float* diag, float scale,
+                                   float* out, long long out_js, long long out_cs, int M, int C,
+                                   int r, int H, int W, int dy, int dx, int in_dtype, void* stream) {
+  return wgrad_launch(S, V, diag, scale, out, out_js, out_cs, M, C, r, H, W, dy, dx, 0.f, nullptr,
+                      in_dtype, stream);
+}
+
+extern "C" int lb_lora_wgrad_masked(const void* S, const float* V, const float* diag, float scale,
+                                    float* out, long long out_js, long long out_cs, int M, int C,
+                                    int r, float drop_p, const void* seed_dev, int in_dtype,
+                                    void* stream) {
+  if (!(drop_p >= 0.f && drop_p < 1.f) || (drop_p > 0.f && seed_dev == nullptr)) return LB_ERR_SHAPE;
+  return wgrad_launch(S, V, diag, scale, out, out_js, out_cs, M, C, r, 0, 0, 0, 0, drop_p, seed_dev,
+                      in_dtype, stream);
+}
+
+static int wgrad_launch(const void* S, const float* V, const float* diag, float scale, float* out,
+                        long long out_js, long long out_cs, int M, int C, int r, int H, int W,
+                        int dy, int dx, float drop_p, const void* seed_dev, int in_dtype,
+                        void* stream) {
+  if (H < 0 || W < 0 || (H > 0) != (W > 0)) return LB_ERR_SHAPE;
+  if (H > 0 && (M % (H * W)) != 0) return LB_ERR_SHAPE;
   if (M <= 0 || C <= 0 || (C % 8) != 0) return LB_ERR_SHAPE;
   if (r < 1 || r > 16) return LB_ERR_RANK;
   if (in_dtype != LB_BF16 && in_dtype != LB_F16) return LB_ERR_DTYPE;
@@ -255,11 +419,46 @@ extern "C" int lb_lora_wgrad(const void* S, const float* V, const float* diag, f
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const uint32_t* S32 = reinterpret_cast<const uint32_t*>(S);
   switch ((r + 3) / 4) {
-    case 1: wgrad_kernel<1><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt); break;
-    case 2: wgrad_kernel<2><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt); break;
-    case 3: wgrad_kernel<3><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt); break;
-    default: wgrad_kernel<4><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt); break;
+    case 1: wgrad_kernel<1><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt, H, W, dy, dx, drop_p, reinterpret_cast<const unsigned long long*>(seed_dev)); break;
+    case 2: wgrad_kernel<2><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt, H, W, dy, dx, drop_p, reinterpret_cast<const unsigned long long*>(seed_dev)); break;
+    case 3: wgrad_kernel<3><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt, H, W, dy, dx, drop_p, reinterpret_cast<const unsigned long long*>(seed_dev)); break;
+    default: wgrad_kernel<4><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt, H, W, dy, dx, drop_p, reinterpret_cast<const unsigned long long*>(seed_dev)); break;
   }
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
+extern "C" int lb_lora_up_dropout(void* Y, int y_dtype, const float* T, const float* up,
+                                  long long up_rs, long long up_cs, const float* diag, float scale,
+                                  float drop_p, const void* seed_dev, int M, int N, int r,
+                                  void* stream) {
+  if (M <= 0 || N <= 0 || (N % 8) != 0) return LB_ERR_SHAPE;
+  if (r < 1 || r > 16) return LB_ERR_RANK;
+  if (!(drop_p >= 0.f && drop_p < 1.f) || seed_dev == nullptr) return LB_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(Y) & 15) return LB_ERR_ALIGN;
+  const long long threads = static_cast<long long>(M) * (N / 8);
+  const int blocks = static_cast<int>((threads + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const unsigned long long* sd = reinterpret_cast<const unsigned long long*>(seed_dev);
+  if (y_dtype == LB_F32)
+    up_dropout_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<float*>(Y), 0, T, up, up_rs, up_cs, diag, scale, drop_p, sd, M, N, r);
+  else if (y_dtype == LB_BF16 || y_dtype == LB_F16)
+    up_dropout_kernel<uint16_t><<<blocks, 256, 0, st>>>(reinterpret_cast<uint16_t*>(Y), y_dtype == LB_BF16, T, up, up_rs, up_cs, diag, scale, drop_p, sd, M, N, r);
+  else
+    return LB_ERR_DTYPE;
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
+extern "C" int lb_lora_dropout_dt(const void* gY, int in_dtype, const float* up, long long up_rs,
+                                  long long up_cs, float drop_p, const void* seed_dev, float* dTs,
+                                  int M, int N, int r, void* stream) {
+  if (M <= 0 || N <= 0 || (N % 8) != 0) return LB_ERR_SHAPE;
+  if (r < 1 || r > 16) return LB_ERR_RANK;
+  if (in_dtype != LB_BF16 && in_dtype != LB_F16) return LB_ERR_DTYPE;
+  if (!(drop_p >= 0.f && drop_p < 1.f) || seed_dev == nullptr) return LB_ERR_SHAPE;
+  const int blocks = (M + 7) / 8;  // 8 warps per block, one row per warp
+  dropout_dt_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const uint32_t*>(gY), in_dtype == LB_BF16, up, up_rs, up_cs, drop_p,
+      reinterpret_cast<const unsigned long long*>(seed_dev), dTs, M, N, r);
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }
 
@@ -297,6 +496,27 @@ extern "C" int lb_cast_weight(const void* src, int src_dtype, void* dst16, void*
     cast_weight_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(src), 0, d, dT, R, C, fmt);
   else if (src_dtype == LB_BF16 || src_dtype == LB_F16)
     cast_weight_kernel<uint16_t><<<grid, block, 0, st>>>(reinterpret_cast<const uint16_t*>(src), src_dtype == LB_BF16, d, dT, R, C, fmt);
+  else
+    return LB_ERR_DTYPE;
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
+extern "C" int lb_cast_conv_weight(const void* src, int src_dtype, void* dst16, void* dstT16,
+                                   int Cout, int Cin, int kh, int kw, int out_dtype,
+                                   void* stream) {
+  if (Cout <= 0 || Cin <= 0 || kh <= 0 || kw <= 0) return LB_ERR_SHAPE;
+  if (out_dtype != LB_BF16 && out_dtype != LB_F16) return LB_ERR_DTYPE;
+  const int T = kh * kw;
+  const long long total = static_cast<long long>(Cout) * Cin * T;
+  const int blocks = static_cast<int>((total + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint16_t* d = reinterpret_cast<uint16_t*>(dst16);
+  uint16_t* dT = reinterpret_cast<uint16_t*>(dstT16);
+  const int fmt = out_dtype == LB_BF16;
+  if (src_dtype == LB_F32)
+    cast_conv_weight_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float*>(src), 0, d, dT, Cout, Cin, T, fmt);
+  else if (src_dtype == LB_BF16 || src_dtype == LB_F16)
+    cast_conv_weight_kernel<uint16_t><<<blocks, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(src), src_dtype == LB_BF16, d, dT, Cout, Cin, T, fmt);
   else
     return LB_ERR_DTYPE;
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;

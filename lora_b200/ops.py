@@ -55,8 +55,10 @@ def cast_weight(w: torch.Tensor, dtype, want_plain: bool, want_t: bool):
 def fused_linear(x2d: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tensor],
                  down16: torch.Tensor, up: torch.Tensor, up_rs: int, up_cs: int,
                  diag: Optional[torch.Tensor], scale: float, r: int, out_dtype,
-                 want_t: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
-    """Y = x2d.w16^T + bias + ((x2d.down16^T) * scale*diag) . up^T ; returns (Y, T or None)."""
+                 want_t: bool, t_in: Optional[torch.Tensor] = None
+                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """Y = x2d.w16^T + bias + ((x2d.down16^T) * scale*diag) . up^T ; returns (Y, T or None).
+    t_in: use these rank-r activations [M,16] instead of x2d.down16^T (dropout backward)."""
     _req_cuda(x2d, w16, down16, up)
     M, K = x2d.shape
     N = w16.shape[0]
@@ -65,7 +67,7 @@ def fused_linear(x2d: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tens
     y = torch.empty((M, N), device=x2d.device, dtype=out_dtype)
     t = torch.empty((M, R_PAD), device=x2d.device, dtype=torch.float32) if want_t else None
     check(_C.lib.lb_lora_linear_fwd(ptr(x2d), ptr(w16), ptr(bias), ptr(down16), ptr(up),
-                                    up_rs, up_cs, ptr(diag), float(scale), ptr(y), ptr(t),
+                                    up_rs, up_cs, ptr(diag), float(scale), ptr(y), ptr(t), ptr(t_in),
                                     M, K, N, r, dtype_code(x2d.dtype), dtype_code(out_dtype),
                                     stream_ptr()), "lb_lora_linear_fwd")
     _count()
@@ -81,4 +83,118 @@ def wgrad(S: torch.Tensor, V: torch.Tensor, diag: Optional[torch.Tensor], scale:
     assert out.dtype == torch.float32
     check(_C.lib.lb_lora_wgrad(ptr(S), ptr(V), ptr(diag), float(scale), ptr(out), out_js, out_cs,
                                M, C, r, dtype_code(S.dtype), stream_ptr()), "lb_lora_wgrad")
+    _count()
+
+
+# ------------------------------------------------------------------------------------ conv path
+def cast_conv_weight(w: torch.Tensor, dtype, want_fwd: bool, want_bwd: bool):
+    """Frozen conv weight [Cout,Cin,kh,kw] -> (forward operand [Cout, kh*kw*Cin] or None,
+    flipped+transposed input-gradient operand [Cin, kh*kw*Cout] or None)."""
+    _req_cuda(w)
+    if not want_fwd and not want_bwd:
+        return None, None
+    w = w.detach().contiguous()
+    cout, cin, kh, kw = w.shape
+    f = torch.empty((cout, kh * kw * cin), device=w.device, dtype=dtype) if want_fwd else None
+    b = torch.empty((cin, kh * kw * cout), device=w.device, dtype=dtype) if want_bwd else None
+    check(_C.lib.lb_cast_conv_weight(ptr(w), dtype_code(w.dtype), ptr(f), ptr(b), cout, cin, kh, kw,
+                                     dtype_code(dtype), stream_ptr()), "lb_cast_conv_weight")
+    _count()
+    return f, b
+
+
+def conv_down16(a4d: torch.Tensor, dtype, table_cache: dict) -> torch.Tensor:
+    """A [r,Cin,kh,kw] fp32 -> [16, kh*kw*Cin] 16-bit with K ordered tap-major, channel-minor."""
+    _req_cuda(a4d)
+    r, cin, kh, kw = a4d.shape
+    taps = kh * kw
+    key = (r, cin, taps, a4d.device)
+    tab = table_cache.get(key)
+    if tab is None:
+        rows = [(t, cin * taps, taps, r, cin, t * cin, taps * cin) for t in range(taps)]
+        tab = torch.tensor(rows, device=a4d.device, dtype=torch.int64)
+        table_cache[key] = tab
+    src = a4d.detach()
+    if src.dtype != torch.float32 or not src.is_contiguous():
+        src = src.float().contiguous()
+    out = torch.empty((R_PAD, taps * cin), device=a4d.device, dtype=dtype)
+    check(_C.lib.lb_refresh_shadows(ptr(src), ptr(tab), taps, cin, ptr(out), dtype_code(dtype),
+                                    stream_ptr()), "lb_refresh_shadows")
+    _count()
+    return out
+
+
+def fused_conv2d(x_nhwc: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tensor],
+                 down16: torch.Tensor, up: torch.Tensor, up_off: int, up_rs: int, up_cs: int,
+                 up_gs: int, diag: Optional[torch.Tensor], scale: float, r: int, cout: int,
+                 kh: int, kw: int, pad_h: int, pad_w: int, per_tap: bool, out_dtype,
+                 want_t: bool, t_in: Optional[torch.Tensor] = None
+                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """x_nhwc: a [N,C,H,W] tensor in channels_last memory format (NHWC bytes). Returns
+    (Y as [N,cout,H,W] channels_last, T [N*H*W,16] or None)."""
+    _req_cuda(x_nhwc, w16, down16, up)
+    n, cin, h, w = x_nhwc.shape
+    assert x_nhwc.is_contiguous(memory_format=torch.channels_last)
+    y = torch.empty((n, cout, h, w), device=x_nhwc.device, dtype=out_dtype,
+                    memory_format=torch.channels_last)
+    t = torch.empty((n * h * w, R_PAD), device=x_nhwc.device, dtype=torch.float32) if want_t else None
+    import ctypes
+    up_ptr = ctypes.c_void_p(up.data_ptr() + 4 * up_off)
+    check(_C.lib.lb_lora_conv2d_fwd(ptr(x_nhwc), ptr(w16), ptr(bias), ptr(down16), up_ptr, up_rs,
+                                    up_cs, up_gs, ptr(diag), float(scale), ptr(y), ptr(t), ptr(t_in),
+                                    n, h, w,
+                                    cin, cout, kh, kw, pad_h, pad_w, r, 1 if per_tap else 0,
+                                    dtype_code(x_nhwc.dtype), dtype_code(out_dtype), stream_ptr()),
+          "lb_lora_conv2d_fwd")
+    _count()
+    return y, t
+
+
+def wgrad_shift(S_rows: torch.Tensor, V: torch.Tensor, diag, scale: float, out: torch.Tensor,
+                out_off: int, out_js: int, out_cs: int, r: int, C: int, H: int, W: int, dy: int,
+                dx: int):
+    """Conv tap of the weight-gradient reduction (see lb_lora_wgrad_shift). S_rows: NHWC bytes."""
+    _req_cuda(S_rows, V, out)
+    M = V.shape[0]
+    import ctypes
+    out_ptr = ctypes.c_void_p(out.data_ptr() + 4 * out_off)
+    check(_C.lib.lb_lora_wgrad_shift(ptr(S_rows), ptr(V), ptr(diag), float(scale), out_ptr, out_js,
+                                     out_cs, M, C, r, H, W, dy, dx, dtype_code(S_rows.dtype),
+                                     stream_ptr()), "lb_lora_wgrad_shift")
+    _count()
+
+
+# ------------------------------------------------------------------------------------ dropout
+def up_dropout_(y2d: torch.Tensor, T: torch.Tensor, up: torch.Tensor, up_rs: int, up_cs: int,
+                diag, scale: float, p: float, seed: torch.Tensor, r: int):
+    """y2d[m,n] += scale/(1-p) * keep(m,n) * sum_j T[m,j] diag[j] up[n,j]   (in place)."""
+    _req_cuda(y2d, T, up, seed)
+    M, N = y2d.shape
+    assert y2d.is_contiguous() and seed.dtype == torch.int64
+    check(_C.lib.lb_lora_up_dropout(ptr(y2d), dtype_code(y2d.dtype), ptr(T), ptr(up), up_rs, up_cs,
+                                    ptr(diag), float(scale), float(p), ptr(seed), M, N, r,
+                                    stream_ptr()), "lb_lora_up_dropout")
+    _count()
+
+
+def dropout_dt(gy2d: torch.Tensor, up: torch.Tensor, up_rs: int, up_cs: int, p: float,
+               seed: torch.Tensor, r: int) -> torch.Tensor:
+    """dTs[m,j] = sum_n keep(m,n)/(1-p) * gY[m,n] * up[n,j]  (fp32 [M,16])."""
+    _req_cuda(gy2d, up, seed)
+    M, N = gy2d.shape
+    out = torch.empty((M, R_PAD), device=gy2d.device, dtype=torch.float32)
+    check(_C.lib.lb_lora_dropout_dt(ptr(gy2d), dtype_code(gy2d.dtype), ptr(up), up_rs, up_cs,
+                                    float(p), ptr(seed), ptr(out), M, N, r, stream_ptr()),
+          "lb_lora_dropout_dt")
+    _count()
+    return out
+
+
+def wgrad_masked(S: torch.Tensor, V: torch.Tensor, diag, scale: float, out: torch.Tensor,
+                 out_js: int, out_cs: int, r: int, p: float, seed: torch.Tensor):
+    _req_cuda(S, V, out, seed)
+    M, C = S.shape
+    check(_C.lib.lb_lora_wgrad_masked(ptr(S), ptr(V), ptr(diag), float(scale), ptr(out), out_js,
+                                      out_cs, M, C, r, float(p), ptr(seed), dtype_code(S.dtype),
+                                      stream_ptr()), "lb_lora_wgrad_masked")
     _count()

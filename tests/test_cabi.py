@@ -26,7 +26,7 @@ def test_build_and_load():
 def test_every_declared_symbol_is_exported():
     from lora_b200 import _C
     names = _declared()
-    assert "lb_lora_linear_fwd" in names and "lb_adamw_clip_step" in names and len(names) >= 7
+    assert "lb_lora_linear_fwd" in names and "lb_adamw_clip_step" in names and len(names) >= 13
     lib = ctypes.CDLL(_C.LIB_PATH)
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/lora_b200.h but not exported"
@@ -39,10 +39,10 @@ def test_argument_validation_without_gpu():
     base = (ctypes.addressof(buf) + 255) & ~255
     p = ctypes.c_void_p(base)
     # rank out of range, bad dtype, misaligned K / pointer: refused before any CUDA call
-    assert L.lb_lora_linear_fwd(p, p, None, p, p, 4, 1, None, 1.0, p, None, 8, 64, 64, 17, 0, 0, None) == -2
-    assert L.lb_lora_linear_fwd(p, p, None, p, p, 4, 1, None, 1.0, p, None, 8, 64, 64, 4, 2, 0, None) == -3
-    assert L.lb_lora_linear_fwd(p, p, None, p, p, 4, 1, None, 1.0, p, None, 8, 60, 64, 4, 0, 0, None) == -1
-    assert L.lb_lora_linear_fwd(ctypes.c_void_p(base + 2), p, None, p, p, 4, 1, None, 1.0, p, None,
+    assert L.lb_lora_linear_fwd(p, p, None, p, p, 4, 1, None, 1.0, p, None, None, 8, 64, 64, 17, 0, 0, None) == -2
+    assert L.lb_lora_linear_fwd(p, p, None, p, p, 4, 1, None, 1.0, p, None, None, 8, 64, 64, 4, 2, 0, None) == -3
+    assert L.lb_lora_linear_fwd(p, p, None, p, p, 4, 1, None, 1.0, p, None, None, 8, 60, 64, 4, 0, 0, None) == -1
+    assert L.lb_lora_linear_fwd(ctypes.c_void_p(base + 2), p, None, p, p, 4, 1, None, 1.0, p, None, None,
                                 8, 64, 64, 4, 0, 0, None) == -4
     assert L.lb_lora_wgrad(p, p, None, 1.0, p, 1, 1, 8, 60, 4, 0, None) == -1
     assert L.lb_lora_wgrad(p, p, None, 1.0, p, 1, 1, 8, 64, 0, 0, None) == -2
