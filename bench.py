@@ -103,7 +103,12 @@ def build_models(device, dtype, seed=0, tiny=False):
         text = build_text_encoder(tiny=tiny)
     unet.requires_grad_(False)
     text.requires_grad_(False)
-    return unet.to(dtype), text.to(dtype)
+    unet, text = unet.to(dtype), text.to(dtype)
+    if torch.device(device).type == "cuda":
+        # NHWC activations/weights for the conv/GroupNorm host layers: cuDNN's tensor-core convs
+        # are NHWC-native (avoids an NCHW<->NHWC transpose around every conv)
+        unet = unet.to(memory_format=torch.channels_last)
+    return unet, text
 
 
 def site_shapes(model, tokens_by_module):

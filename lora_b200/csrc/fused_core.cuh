@@ -82,8 +82,8 @@ struct Smem {
   static_assert(ACC_COLS <= 512, "TMEM budget exceeded");
 };
 
-template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G, int MIN_CTAS = 1>
+__global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
 fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY,
                   const FusedParams p) {

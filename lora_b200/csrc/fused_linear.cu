@@ -7,11 +7,12 @@
 
 namespace lb {
 
-template <int BLOCK_N, int STAGES, typename OutT>
+template <int BLOCK_N, int STAGES, typename OutT, int MIN_CTAS>
 static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, const FusedParams& p,
                          int out_dtype, cudaStream_t stream) {
   using S = Smem<BLOCK_N, STAGES, OutT, 1>;
-  auto kern = fused_lora_kernel<BLOCK_N, STAGES, OutT, false, 1>;
+  auto kern = fused_lora_kernel<BLOCK_N, STAGES, OutT, false, 1, MIN_CTAS>;
+  static_assert(MIN_CTAS * (S::DYN_BYTES + 1024) <= 233472 && MIN_CTAS * S::TMEM_COLS <= 512, "occupancy target does not fit");
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES) != cudaSuccess)
@@ -58,10 +59,13 @@ extern "C" int lb_lora_linear_fwd(const void* X, const void* W, const float* bia
 
   const long long tiles128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
   const bool narrow = tiles128 < 120;  // not enough 128-wide tiles to fill 148 SMs: halve BLOCK_N
+  // Two (BLOCK_N = 128) or three (BLOCK_N = 64) CTAs per SM: the K loops of the SD1.5 sites are
+  // only 5-20 steps long, so one CTA's epilogue (TMEM drain + store) overlaps its neighbours'
+  // TMA/MMA phase instead of leaving the SM idle. (fp32 output needs a 64 KB staging tile: 1 CTA.)
   if (out_dtype == LB_F32) {
-    return narrow ? launch_linear<64, 4, float>(X, W, down16, Y, p, out_dtype, st)
-                  : launch_linear<128, 4, float>(X, W, down16, Y, p, out_dtype, st);
+    return narrow ? launch_linear<64, 3, float, 2>(X, W, down16, Y, p, out_dtype, st)
+                  : launch_linear<128, 4, float, 1>(X, W, down16, Y, p, out_dtype, st);
   }
-  return narrow ? launch_linear<64, 4, uint16_t>(X, W, down16, Y, p, out_dtype, st)
-                : launch_linear<128, 4, uint16_t>(X, W, down16, Y, p, out_dtype, st);
+  return narrow ? launch_linear<64, 2, uint16_t, 3>(X, W, down16, Y, p, out_dtype, st)
+                : launch_linear<128, 2, uint16_t, 2>(X, W, down16, Y, p, out_dtype, st);
 }

@@ -46,75 +46,89 @@ __device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long
 }
 
 // ------------------------------------------------------------------------------- wgrad
-// CTA = 8 warps over a [ROWS x 64-column] slab of S. Lane owns 2 adjacent columns (one 32-bit
-// load; a warp reads one full 128-B line per row). Warps stride over rows. Each thread keeps
-// 16 x 2 fp32 partial sums; warps are combined through shared memory; one atomicAdd per output.
-constexpr int WG_COLS = 64;
+// out[j, c] += coef_j * sum_m V[m, j] * S[m, c]   -- a [r x M] . [M x C] product with r <= 16:
+// pure streaming over S (HBM/L2-bound), so the kernel is organised for memory-level parallelism:
+// CTA = 8 warps over a [64-row x 128-column] slab; a lane owns 4 adjacent columns (one 8-byte
+// load; a warp covers 256 B of a row), a warp owns 8 rows and issues all 8 row loads before the
+// first FMA. Partials are combined with shared-memory atomics, then one global atomicAdd per
+// output element per CTA.
+constexpr int WG_COLS = 128;
 constexpr int WG_WARPS = 8;
-constexpr int WG_ROWS = 256;
+constexpr int WG_RPW = 8;                    // rows per warp
+constexpr int WG_ROWS = WG_WARPS * WG_RPW;   // 64 rows per CTA
 
 template <int RQ>  // number of float4 groups of V actually used: ceil(r/4)
 __global__ void __launch_bounds__(WG_WARPS * 32)
-wgrad_kernel(const uint32_t* __restrict__ S, const float* __restrict__ V,
+wgrad_kernel(const uint2* __restrict__ S, const float* __restrict__ V,
              const float* __restrict__ diag, float scale, float* __restrict__ out,
              long long out_js, long long out_cs, int M, int C, int r, int fmt, int cH, int cW,
              int dy, int dx, float drop_p, const unsigned long long* __restrict__ seed_dev) {
-  __shared__ float red[WG_WARPS][RQ * 4][WG_COLS];
+  __shared__ float red[RQ * 4][WG_COLS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c0 = blockIdx.x * WG_COLS + lane * 2;
-  const int m_begin = blockIdx.y * WG_ROWS;
-  const int m_end = min(M, m_begin + WG_ROWS);
-  const bool col_ok = c0 < C;  // C is even (C % 8 == 0 enforced by the host)
-  const size_t pitch = static_cast<size_t>(C) >> 1;  // row pitch in 32-bit words
+  const int c0 = blockIdx.x * WG_COLS + lane * 4;
+  const int m_base = blockIdx.y * WG_ROWS + warp * WG_RPW;
+  const bool col_ok = c0 < C;                          // C % 8 == 0 => whole 4-column group valid
+  const size_t pitch = static_cast<size_t>(C) >> 2;    // row pitch in 8-byte words
+  for (int i = threadIdx.x; i < RQ * 4 * WG_COLS; i += WG_WARPS * 32) (&red[0][0])[i] = 0.f;
+  __syncthreads();
 
-  float acc[RQ * 4][2];
+  uint2 raw[WG_RPW];
 #pragma unroll
-  for (int j = 0; j < RQ * 4; ++j) acc[j][0] = acc[j][1] = 0.f;
-
-  for (int m = m_begin + warp; m < m_end; m += WG_WARPS) {
-    // conv weight-gradient taps: row m is pixel (h, w) of an NHWC image; S is read at the pixel
-    // shifted by (dy, dx), zero outside the image (= the convolution's padding)
+  for (int i = 0; i < WG_RPW; ++i) {
+    const int m = m_base + i;
+    bool ok = col_ok && m < M;
     long long src = m;
-    bool ok = col_ok;
-    if (cH > 0) {
+    if (cH > 0 && ok) {
+      // conv weight-gradient tap: row m is pixel (h, w) of an NHWC image; S is read at the pixel
+      // shifted by (dy, dx), zero outside the image (= the convolution's zero padding)
       const int ww = m % cW + dx, hh = (m / cW) % cH + dy;
-      ok = ok && hh >= 0 && hh < cH && ww >= 0 && ww < cW;
+      ok = hh >= 0 && hh < cH && ww >= 0 && ww < cW;
       src = static_cast<long long>(m) + dy * cW + dx;
     }
-    const uint32_t w = ok ? __ldg(S + static_cast<size_t>(src) * pitch + (c0 >> 1)) : 0u;
-    float2 x = ld16x2(w, fmt);
+    raw[i] = ok ? __ldg(S + static_cast<size_t>(src) * pitch + (c0 >> 2)) : make_uint2(0u, 0u);
+  }
+  float acc[RQ * 4][4];
+#pragma unroll
+  for (int j = 0; j < RQ * 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+  const unsigned long long sd = (drop_p > 0.f) ? seed_dev[0] : 0ull;
+  const float inv = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
+#pragma unroll
+  for (int i = 0; i < WG_RPW; ++i) {
+    const int m = m_base + i;
+    if (m >= M) break;
+    float2 a = ld16x2(raw[i].x, fmt), b = ld16x2(raw[i].y, fmt);
+    float x[4] = {a.x, a.y, b.x, b.y};
     if (drop_p > 0.f) {  // S = gY of a dropout site: the branch saw mask/(1-p)
-      const unsigned long long sd = seed_dev[0];
       const unsigned long long e = static_cast<unsigned long long>(m) * C + c0;
-      const float inv = 1.f / (1.f - drop_p);
-      x.x = drop_keep(sd, e, drop_p) ? x.x * inv : 0.f;
-      x.y = drop_keep(sd, e + 1, drop_p) ? x.y * inv : 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) x[k] = drop_keep(sd, e + k, drop_p) ? x[k] * inv : 0.f;
     }
     const float4* vrow = reinterpret_cast<const float4*>(V + static_cast<size_t>(m) * 16);
 #pragma unroll
     for (int qd = 0; qd < RQ; ++qd) {
       const float4 v = __ldg(vrow + qd);
-      acc[qd * 4 + 0][0] += v.x * x.x; acc[qd * 4 + 0][1] += v.x * x.y;
-      acc[qd * 4 + 1][0] += v.y * x.x; acc[qd * 4 + 1][1] += v.y * x.y;
-      acc[qd * 4 + 2][0] += v.z * x.x; acc[qd * 4 + 2][1] += v.z * x.y;
-      acc[qd * 4 + 3][0] += v.w * x.x; acc[qd * 4 + 3][1] += v.w * x.y;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[qd * 4 + 0][k] += v.x * x[k];
+        acc[qd * 4 + 1][k] += v.y * x[k];
+        acc[qd * 4 + 2][k] += v.z * x[k];
+        acc[qd * 4 + 3][k] += v.w * x[k];
+      }
     }
   }
+  if (col_ok) {
 #pragma unroll
-  for (int j = 0; j < RQ * 4; ++j) {
-    red[warp][j][lane * 2 + 0] = acc[j][0];
-    red[warp][j][lane * 2 + 1] = acc[j][1];
+    for (int j = 0; j < RQ * 4; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) atomicAdd(&red[j][lane * 4 + k], acc[j][k]);
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < RQ * 4 * WG_COLS; idx += WG_WARPS * 32) {
     const int j = idx / WG_COLS, c = idx % WG_COLS;
     const int cg = blockIdx.x * WG_COLS + c;
     if (j < r && cg < C) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < WG_WARPS; ++w) s += red[w][j][c];
       const float coef = scale * (diag ? diag[j] : 1.f);
-      atomicAdd(out + j * out_js + cg * out_cs, coef * s);
+      atomicAdd(out + j * out_js + cg * out_cs, coef * red[j][c]);
     }
   }
 }
@@ -417,7 +431,7 @@ static int wgrad_launch(const void* S, const float* V, const float* diag, float 
   const int fmt = in_dtype == LB_BF16 ? 1 : 0;
   dim3 grid((C + WG_COLS - 1) / WG_COLS, (M + WG_ROWS - 1) / WG_ROWS);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const uint32_t* S32 = reinterpret_cast<const uint32_t*>(S);
+  const uint2* S32 = reinterpret_cast<const uint2*>(S);
   switch ((r + 3) / 4) {
     case 1: wgrad_kernel<1><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt, H, W, dy, dx, drop_p, reinterpret_cast<const unsigned long long*>(seed_dev)); break;
     case 2: wgrad_kernel<2><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt, H, W, dy, dx, drop_p, reinterpret_cast<const unsigned long long*>(seed_dev)); break;

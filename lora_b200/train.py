@@ -89,7 +89,8 @@ class LoraTrainStep:
             else:
                 with torch.no_grad():
                     ehs = self.text_encoder(self.input_ids)[0]
-            pred = self.unet(noisy.to(self.model_dtype), timesteps, ehs.to(self.model_dtype)).sample
+            noisy = noisy.to(self.model_dtype).contiguous(memory_format=torch.channels_last)
+            pred = self.unet(noisy, timesteps, ehs.to(self.model_dtype)).sample
         loss = F.mse_loss(pred.float(), noise.float(), reduction="mean")
         loss.backward()
         self.arena.allreduce_grads()

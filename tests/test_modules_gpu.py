@@ -254,4 +254,7 @@ def test_training_step_cuda_graph_equals_eager():
         torch.cuda.synchronize()
         losses.append(out)
     assert all(l == l and l > 0 for l in losses[0] + losses[1])   # finite, positive
-    assert int(tr.arena.step_dev) == 6
+    # graph path: 1 warm-up step executed + capture (recorded, not executed) + 4 replays
+    assert int(tr.arena.step_dev) == 5
+    # both paths train: the loss on the fixed sample/noise distribution stays in a sane range
+    assert max(losses[0] + losses[1]) < 10.0
