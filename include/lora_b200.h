@@ -56,6 +56,10 @@ int lb_lora_linear_fwd(const void* X, const void* W, const float* bias, const vo
                        float scale, void* Y, float* T_out, const float* T_in, int M, int K, int N,
                        int r, int in_dtype, int out_dtype, void* stream);
 
+/* Benchmark/profiling knob: tile schedule of lb_lora_linear_fwd. 0 = auto (default),
+ * 1 = one tile per CTA, 2 = persistent CTAs with double-buffered TMEM accumulators. */
+int lb_debug_set_linear_mode(int mode);
+
 /* Skinny weight-gradient reduction (streams S once, fp32 atomics into out):
  *     out[j*out_js + c*out_cs] += scale * diag[j] * sum_m V[m,j] * S[m,c]     j < r, c < C
  * dA[r,K]: S = X[M,K],  V = gY.B (T_out of the dX call), out_js = K, out_cs = 1

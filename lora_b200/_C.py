@@ -39,6 +39,7 @@ def _load():
         "lb_adamw_clip_step": ([vp, vp, vp, vp, ll, ctypes.POINTER(ll), i32, vp, f32, f32, f32,
                                 f32, f32, f32, vp, vp, vp, vp], i32),
         "lb_refresh_shadows": ([vp, vp, i32, i32, vp, i32, vp], i32),
+        "lb_debug_set_linear_mode": ([i32], i32),
         "lb_lora_wgrad_shift": ([vp, vp, vp, f32, vp, ll, ll, i32, i32, i32, i32, i32, i32, i32,
                                  i32, vp], i32),
         "lb_lora_conv2d_fwd": ([vp, vp, vp, vp, vp, ll, ll, ll, vp, f32, vp, vp, vp,

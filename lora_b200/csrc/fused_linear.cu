@@ -2,6 +2,7 @@
 // Replaces LoraInjectedLinear.forward (/root/reference/lora_diffusion/lora.py:53-58) and the dX
 // part of its autograd backward. Kernel: fused_core.cuh.
 #include "fused_core.cuh"
+#include "fused_persistent.cuh"
 #include "lora_b200.h"
 #include "tmap.h"
 
@@ -31,7 +32,45 @@ static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, 
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }
 
+template <int BLOCK_N, int STAGES, typename OutT>
+static int launch_persistent(const void* X, const void* W, const void* Dn, void* Y,
+                             const FusedParams& p, int out_dtype, cudaStream_t stream) {
+  using S = PSmem<BLOCK_N, STAGES, OutT>;
+  auto kern = fused_lora_persistent_kernel<BLOCK_N, STAGES, OutT>;
+  static bool attr_set = false;
+  static int num_sms = 0;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES) != cudaSuccess)
+      return LB_ERR_CUDA;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
+      return LB_ERR_CUDA;
+    attr_set = true;
+  }
+  const CUtensorMapDataType in_dt = p.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
+  CUtensorMap tmX, tmW, tmD, tmY;
+  if (!tmap_2d(&tmX, X, in_dt, 2, p.K, p.M, BLOCK_K, BLOCK_M, true)) return LB_ERR_TMAP;
+  if (!tmap_2d(&tmW, W, in_dt, 2, p.K, p.N, BLOCK_K, BLOCK_N, true)) return LB_ERR_TMAP;
+  if (!tmap_2d(&tmD, Dn, in_dt, 2, p.K, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
+  if (!tmap_2d(&tmY, Y, out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
+  const long long total = static_cast<long long>((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + BLOCK_M - 1) / BLOCK_M);
+  const int grid = static_cast<int>(total < num_sms ? total : num_sms);
+  kern<<<grid, NUM_THREADS, S::DYN_BYTES, stream>>>(tmX, tmW, tmD, tmY, p);
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
+static int g_linear_mode = 0;  // 0 = auto, 1 = one tile per CTA (2-3 CTAs/SM), 2 = persistent
+
 }  // namespace lb
+
+// Tuning knob (benchmarks / profiling only): force the tile schedule of lb_lora_linear_fwd.
+extern "C" int lb_debug_set_linear_mode(int mode) {
+  if (mode < 0 || mode > 11) return LB_ERR_SHAPE;   // schedule + 4 * block_n choice (0 auto, 1: 64, 2: 128)
+  lb::g_linear_mode = mode;
+  return LB_OK;
+}
 
 extern "C" int lb_lora_linear_fwd(const void* X, const void* W, const float* bias,
                                   const void* down16, const float* up, long long up_rs,
@@ -57,8 +96,23 @@ extern "C" int lb_lora_linear_fwd(const void* X, const void* W, const float* bia
   p.fmt = (in_dtype == LB_BF16) ? 1 : 0; p.t_group = 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
+  const int sched = g_linear_mode & 3, bn_choice = g_linear_mode >> 2;
   const long long tiles128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
-  const bool narrow = tiles128 < 120;  // not enough 128-wide tiles to fill 148 SMs: halve BLOCK_N
+  bool narrow = tiles128 < 120;  // not enough 128-wide tiles to fill 148 SMs: halve BLOCK_N
+  if (bn_choice == 1) narrow = true;
+  if (bn_choice == 2) narrow = false;
+  // More tiles than SMs: persistent CTAs with a double-buffered TMEM accumulator (epilogue of
+  // tile i overlaps the main loop of tile i+1). Otherwise one tile per CTA.
+  const long long tiles_n = narrow ? static_cast<long long>((M + 127) / 128) * ((N + 63) / 64) : tiles128;
+  const bool persistent = sched == 2 || (sched == 0 && tiles_n >= 3 * 148);
+  if (persistent) {
+    if (out_dtype == LB_F32) {
+      return narrow ? launch_persistent<64, 4, float>(X, W, down16, Y, p, out_dtype, st)
+                    : launch_persistent<128, 4, float>(X, W, down16, Y, p, out_dtype, st);
+    }
+    return narrow ? launch_persistent<64, 6, uint16_t>(X, W, down16, Y, p, out_dtype, st)
+                  : launch_persistent<128, 4, uint16_t>(X, W, down16, Y, p, out_dtype, st);
+  }
   // Two (BLOCK_N = 128) or three (BLOCK_N = 64) CTAs per SM: the K loops of the SD1.5 sites are
   // only 5-20 steps long, so one CTA's epilogue (TMEM drain + store) overlaps its neighbours'
   // TMA/MMA phase instead of leaving the SM idle. (fp32 output needs a 64 KB staging tile: 1 CTA.)
