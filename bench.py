@@ -205,13 +205,16 @@ def run_native(args):
     res = args.res
     L_lat = res // 8
     unet, text = build_models(dev, dt, seed=0, tiny=args.tiny)
-    L.inject_trainable_lora(unet, r=args.rank)
+    if args.extended:   # configs[2]: --use_extended_lora (ResnetBlock2D conv sites; class-default dropout 0.1)
+        L.inject_trainable_lora_extended(unet, r=args.rank)
+    else:
+        L.inject_trainable_lora(unet, r=args.rank)
     L.inject_trainable_lora(text, target_replace_module={"CLIPAttention"}, r=args.rank)
     # reference init has up = 0 (lora.py:51); give the up factors small non-zero values so the
     # LoRA branch and all three gradients are numerically exercised
     g = torch.Generator(device=dev).manual_seed(1)
     for m in list(unet.modules()) + list(text.modules()):
-        if type(m).__name__ == "LoraInjectedLinear":
+        if type(m).__name__ in ("LoraInjectedLinear", "LoraInjectedConv2d"):
             m.lora_up.weight.data.normal_(0.0, 0.01, generator=g)
 
     cfg = StepConfig(compute_dtype=dt, use_cuda_graph=not args.no_graph)
@@ -290,7 +293,10 @@ def run_native(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic latents/token ids, random-init SD1.5-shaped weights",
-            "config": {"workload": WORKLOAD if not args.tiny else "TINY smoke config (not a bench)",
+            "config": {"workload": ("TINY smoke config (not a bench)" if args.tiny else
+                                    (WORKLOAD if not args.extended else
+                                     "SD1.5 --use_extended_lora (ResBlock Conv2d LoRA, dropout 0.1) UNet+text_encoder 512x512 bf16 bs=1/GPU (configs[2] shape)")),
+                       "extended": bool(args.extended),
                        "resolution": res, "rank": args.rank, "global_batch": world,
                        "lora_sites": len(shapes), "lora_params": trainer.arena.n_params,
                        "parallelism": f"dp{world}", "cuda_graph": trainer.graph is not None,
@@ -381,6 +387,7 @@ def main():
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--rank", type=int, default=4)
     ap.add_argument("--tiny", action="store_true", help="toy widths (smoke only, not a bench)")
+    ap.add_argument("--extended", action="store_true", help="configs[2]: extended (conv) LoRA sites")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=0, help="run N eager steps and exit (for ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -70,6 +70,15 @@ int lb_lora_wgrad(const void* S, const float* V, const float* diag, float scale,
                   long long out_js, long long out_cs, int M, int C, int r, int in_dtype,
                   void* stream);
 
+/* Both factor gradients of one linear site in ONE launch (the two reductions are independent):
+ *   dA[j*dA_js + k*dA_cs] += scale*diag[j] * sum_m dTs[m,j] * X[m,k]      k < K
+ *   dB[j*dB_js + n*dB_cs] += scale*diag[j] * sum_m T[m,j]  * gY[m,n]      n < N
+ * drop_p > 0: gY is masked like in lb_lora_wgrad_masked (mask index m*N + n). */
+int lb_lora_wgrad_pair(const void* X, const float* dTs, float* dA, long long dA_js, long long dA_cs,
+                       int K, const void* gY, const float* T, float* dB, long long dB_js,
+                       long long dB_cs, int N, const float* diag, float scale, int M, int r,
+                       float drop_p, const void* seed_dev, int in_dtype, void* stream);
+
 /* Conv tap of the same reduction: rows of S are the pixels of NHWC images [M/(H*W), H, W, C]; S is
  * read at pixel (h+dy, w+dx), zero outside the image (the convolution's zero padding):
  *     out[...] += scale * diag[j] * sum_p V[p,j] * S[p shifted by (dy,dx), c]
@@ -157,6 +166,30 @@ int lb_adamw_clip_step(float* p, float* g, float* m, float* v, long long n,
  * (conv down factors use one entry per filter tap so that K is ordered tap-major, channel-minor) */
 int lb_refresh_shadows(const float* p, const long long* table, int n_entries, int max_C,
                        void* dst16_base, int out_dtype, void* stream);
+
+/* ---- batched truncated SVD for LoRA distillation (replaces the serial torch.linalg.svd loop of
+ * lora_diffusion/cli_svd.py:24-92). Randomized range finder with 32 probe vectors on
+ * dW[b] = Wt[b] - Wb[b] (N x K, row-major, LB_F32/LB_BF16/LB_F16). Wt/Wb are DEVICE arrays of `batch` device pointers to same-shape
+ * matrices. Tall-skinny operands are fp32 row-major [batch, rows, 32]. See lora_b200/svd.py for
+ * the driver (probe -> power iterations with CholeskyQR2 -> 32x32 Jacobi -> factors). */
+/* transpose = 0: out[b] (N x 32) = dW[b] . in[b] (K x 32);  1: out[b] (K x 32) = dW[b]^T . in[b] (N x 32) */
+int lb_svd_mul(const void* const* Wt, const void* const* Wb, int w_dtype, const float* in, float* out,
+               int N, int K, int batch, int transpose, void* stream);
+/* G[b] (32x32) = Y[b]^T Y[b] */
+int lb_svd_gram(const float* Y, float* G, int rows, int batch, void* stream);
+/* G = R^T R (upper R, tiny ridge) -> Rinv[b] = R^-1 (32x32) */
+int lb_svd_chol_inv(const float* G, float* Rinv, int batch, void* stream);
+/* out[b] = Y[b] (rows x 32) . M[b] (32x32), first out_cols columns, optionally column-scaled
+ * (scale_mode 1: * colscale[b][j], 2: / colscale[b][j]); out may alias Y; transposed = 1 writes
+ * out[b][j*out_pitch + row]. */
+int lb_svd_apply(const float* Y, const float* M, const float* colscale, int scale_mode, float* out,
+                 int rows, int out_cols, long long out_pitch, int transposed,
+                 long long out_batch_stride, int batch, void* stream);
+/* symmetric 32x32 eigen-decomposition (cyclic Jacobi): V columns sorted by descending eigenvalue,
+ * sigma = sqrt(max(eig, 0)) */
+int lb_svd_jacobi(const float* G, float* V, float* sigma, int batch, int sweeps, void* stream);
+/* standard-normal probes from a counter hash */
+int lb_svd_randn(float* out, long long n, unsigned long long seed, void* stream);
 
 #ifdef __cplusplus
 }

@@ -113,13 +113,18 @@ extern "C" int lb_lora_linear_fwd(const void* X, const void* W, const float* bia
     return narrow ? launch_persistent<64, 6, uint16_t>(X, W, down16, Y, p, out_dtype, st)
                   : launch_persistent<128, 4, uint16_t>(X, W, down16, Y, p, out_dtype, st);
   }
-  // Two (BLOCK_N = 128) or three (BLOCK_N = 64) CTAs per SM: the K loops of the SD1.5 sites are
-  // only 5-20 steps long, so one CTA's epilogue (TMEM drain + store) overlaps its neighbours'
-  // TMA/MMA phase instead of leaving the SM idle. (fp32 output needs a 64 KB staging tile: 1 CTA.)
+  // One tile per CTA. More tiles than SMs: 2 (BLOCK_N = 128) or 3 (BLOCK_N = 64) CTAs per SM with
+  // a short smem ring, so one CTA's drain overlaps its neighbours' loads. Fewer tiles than SMs
+  // (small-M / long-K sites): one CTA per SM with a DEEP ring (7 x 26 KB or 4 x 34 KB in flight),
+  // because a lone CTA streaming K = 768..10240 is bound by load latency, not bandwidth.
+  const bool crowded = tiles_n > 148;
   if (out_dtype == LB_F32) {
     return narrow ? launch_linear<64, 3, float, 2>(X, W, down16, Y, p, out_dtype, st)
                   : launch_linear<128, 4, float, 1>(X, W, down16, Y, p, out_dtype, st);
   }
-  return narrow ? launch_linear<64, 2, uint16_t, 3>(X, W, down16, Y, p, out_dtype, st)
-                : launch_linear<128, 2, uint16_t, 2>(X, W, down16, Y, p, out_dtype, st);
+  if (narrow)
+    return crowded ? launch_linear<64, 2, uint16_t, 3>(X, W, down16, Y, p, out_dtype, st)
+                   : launch_linear<64, 7, uint16_t, 1>(X, W, down16, Y, p, out_dtype, st);
+  return crowded ? launch_linear<128, 2, uint16_t, 2>(X, W, down16, Y, p, out_dtype, st)
+                 : launch_linear<128, 4, uint16_t, 1>(X, W, down16, Y, p, out_dtype, st);
 }

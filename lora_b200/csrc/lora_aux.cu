@@ -57,64 +57,99 @@ constexpr int WG_WARPS = 8;
 constexpr int WG_RPW = 8;                    // rows per warp
 constexpr int WG_ROWS = WG_WARPS * WG_RPW;   // 64 rows per CTA
 
+struct WgProblem {
+  const uint2* S;      // [M, C] 16-bit rows (8-byte words)
+  const float* V;      // [M, 16] fp32
+  float* out;          // out[j*js + c*cs]
+  long long js, cs;
+  int C;
+  float drop_p;        // > 0: S is masked (dropout site), mask index m*C + c
+};
+struct WgArgs {
+  WgProblem pr[2];     // dA and dB of one site share a launch (pr[1].C == 0: single problem)
+  const float* diag;
+  const unsigned long long* seed_dev;
+  float scale;
+  int M, r, fmt;
+  int cH, cW, dy, dx;  // conv tap shift of problem 0 (cH == 0: none)
+  int slabs;           // 64-row slabs per CTA
+};
+
 template <int RQ>  // number of float4 groups of V actually used: ceil(r/4)
 __global__ void __launch_bounds__(WG_WARPS * 32)
-wgrad_kernel(const uint2* __restrict__ S, const float* __restrict__ V,
-             const float* __restrict__ diag, float scale, float* __restrict__ out,
-             long long out_js, long long out_cs, int M, int C, int r, int fmt, int cH, int cW,
-             int dy, int dx, float drop_p, const unsigned long long* __restrict__ seed_dev) {
+wgrad_kernel(const WgArgs a) {
   __shared__ float red[RQ * 4][WG_COLS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c0 = blockIdx.x * WG_COLS + lane * 4;
-  const int m_base = blockIdx.y * WG_ROWS + warp * WG_RPW;
+  const int nb0 = (a.pr[0].C + WG_COLS - 1) / WG_COLS;
+  const int which = (static_cast<int>(blockIdx.x) >= nb0) ? 1 : 0;
+  const WgProblem& P = a.pr[which];
+  const int cblk = which ? blockIdx.x - nb0 : blockIdx.x;
+  const int C = P.C;
+  const int c0 = cblk * WG_COLS + lane * 4;
   const bool col_ok = c0 < C;                          // C % 8 == 0 => whole 4-column group valid
   const size_t pitch = static_cast<size_t>(C) >> 2;    // row pitch in 8-byte words
+  const int cH = which ? 0 : a.cH;
   for (int i = threadIdx.x; i < RQ * 4 * WG_COLS; i += WG_WARPS * 32) (&red[0][0])[i] = 0.f;
   __syncthreads();
 
-  uint2 raw[WG_RPW];
-#pragma unroll
-  for (int i = 0; i < WG_RPW; ++i) {
-    const int m = m_base + i;
-    bool ok = col_ok && m < M;
-    long long src = m;
-    if (cH > 0 && ok) {
-      // conv weight-gradient tap: row m is pixel (h, w) of an NHWC image; S is read at the pixel
-      // shifted by (dy, dx), zero outside the image (= the convolution's zero padding)
-      const int ww = m % cW + dx, hh = (m / cW) % cH + dy;
-      ok = hh >= 0 && hh < cH && ww >= 0 && ww < cW;
-      src = static_cast<long long>(m) + dy * cW + dx;
-    }
-    raw[i] = ok ? __ldg(S + static_cast<size_t>(src) * pitch + (c0 >> 2)) : make_uint2(0u, 0u);
-  }
   float acc[RQ * 4][4];
 #pragma unroll
   for (int j = 0; j < RQ * 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-  const unsigned long long sd = (drop_p > 0.f) ? seed_dev[0] : 0ull;
+  const float drop_p = P.drop_p;
+  const unsigned long long sd = (drop_p > 0.f) ? a.seed_dev[0] : 0ull;
   const float inv = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
+
+  auto load_rows = [&](int m_base, uint2 (&raw)[WG_RPW]) {
 #pragma unroll
-  for (int i = 0; i < WG_RPW; ++i) {
-    const int m = m_base + i;
-    if (m >= M) break;
-    float2 a = ld16x2(raw[i].x, fmt), b = ld16x2(raw[i].y, fmt);
-    float x[4] = {a.x, a.y, b.x, b.y};
-    if (drop_p > 0.f) {  // S = gY of a dropout site: the branch saw mask/(1-p)
-      const unsigned long long e = static_cast<unsigned long long>(m) * C + c0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) x[k] = drop_keep(sd, e + k, drop_p) ? x[k] * inv : 0.f;
+    for (int i = 0; i < WG_RPW; ++i) {
+      const int m = m_base + i;
+      bool ok = col_ok && m < a.M;
+      long long src = m;
+      if (cH > 0 && ok) {
+        // conv weight-gradient tap: row m is pixel (h, w) of an NHWC image; S is read at the pixel
+        // shifted by (dy, dx), zero outside the image (= the convolution's zero padding)
+        const int ww = m % a.cW + a.dx, hh = (m / a.cW) % cH + a.dy;
+        ok = hh >= 0 && hh < cH && ww >= 0 && ww < a.cW;
+        src = static_cast<long long>(m) + a.dy * a.cW + a.dx;
+      }
+      raw[i] = ok ? __ldg(P.S + static_cast<size_t>(src) * pitch + (c0 >> 2)) : make_uint2(0u, 0u);
     }
-    const float4* vrow = reinterpret_cast<const float4*>(V + static_cast<size_t>(m) * 16);
+  };
+
+  const int m_first = blockIdx.y * a.slabs * WG_ROWS + warp * WG_RPW;
+  uint2 cur[WG_RPW], nxt[WG_RPW];
+  load_rows(m_first, cur);
+  for (int sl = 0; sl < a.slabs; ++sl) {
+    const int m_base = m_first + sl * WG_ROWS;
+    if (m_base >= a.M) break;
+    if (sl + 1 < a.slabs) load_rows(m_base + WG_ROWS, nxt);   // next slab's rows in flight
 #pragma unroll
-    for (int qd = 0; qd < RQ; ++qd) {
-      const float4 v = __ldg(vrow + qd);
+    for (int i = 0; i < WG_RPW; ++i) {
+      const int m = m_base + i;
+      if (m < a.M) {
+        float2 lo = ld16x2(cur[i].x, a.fmt), hi = ld16x2(cur[i].y, a.fmt);
+        float x[4] = {lo.x, lo.y, hi.x, hi.y};
+        if (drop_p > 0.f) {  // S = gY of a dropout site: the branch saw mask/(1-p)
+          const unsigned long long e = static_cast<unsigned long long>(m) * C + c0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        acc[qd * 4 + 0][k] += v.x * x[k];
-        acc[qd * 4 + 1][k] += v.y * x[k];
-        acc[qd * 4 + 2][k] += v.z * x[k];
-        acc[qd * 4 + 3][k] += v.w * x[k];
+          for (int k = 0; k < 4; ++k) x[k] = drop_keep(sd, e + k, drop_p) ? x[k] * inv : 0.f;
+        }
+        const float4* vrow = reinterpret_cast<const float4*>(P.V + static_cast<size_t>(m) * 16);
+#pragma unroll
+        for (int qd = 0; qd < RQ; ++qd) {
+          const float4 v = __ldg(vrow + qd);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            acc[qd * 4 + 0][k] += v.x * x[k];
+            acc[qd * 4 + 1][k] += v.y * x[k];
+            acc[qd * 4 + 2][k] += v.z * x[k];
+            acc[qd * 4 + 3][k] += v.w * x[k];
+          }
+        }
       }
     }
+#pragma unroll
+    for (int i = 0; i < WG_RPW; ++i) cur[i] = nxt[i];
   }
   if (col_ok) {
 #pragma unroll
@@ -125,10 +160,10 @@ wgrad_kernel(const uint2* __restrict__ S, const float* __restrict__ V,
   __syncthreads();
   for (int idx = threadIdx.x; idx < RQ * 4 * WG_COLS; idx += WG_WARPS * 32) {
     const int j = idx / WG_COLS, c = idx % WG_COLS;
-    const int cg = blockIdx.x * WG_COLS + c;
-    if (j < r && cg < C) {
-      const float coef = scale * (diag ? diag[j] : 1.f);
-      atomicAdd(out + j * out_js + cg * out_cs, coef * red[j][c]);
+    const int cg = cblk * WG_COLS + c;
+    if (j < a.r && cg < C) {
+      const float coef = a.scale * (a.diag ? a.diag[j] : 1.f);
+      atomicAdd(P.out + j * P.js + cg * P.cs, coef * red[j][c]);
     }
   }
 }
@@ -418,27 +453,65 @@ extern "C" int lb_lora_wgrad_masked(const void* S, const float* V, const float* 
                       in_dtype, stream);
 }
 
+static int wgrad_run(WgArgs& a, int in_dtype, void* stream) {
+  if (a.M <= 0) return LB_ERR_SHAPE;
+  if (a.r < 1 || a.r > 16) return LB_ERR_RANK;
+  if (in_dtype != LB_BF16 && in_dtype != LB_F16) return LB_ERR_DTYPE;
+  int nblk = 0;
+  for (int i = 0; i < 2; ++i) {
+    const WgProblem& P = a.pr[i];
+    if (P.C == 0 && i == 1) continue;
+    if (P.C <= 0 || (P.C % 8) != 0) return LB_ERR_SHAPE;
+    if ((reinterpret_cast<uintptr_t>(P.S) | reinterpret_cast<uintptr_t>(P.V)) & 15) return LB_ERR_ALIGN;
+    nblk += (P.C + WG_COLS - 1) / WG_COLS;
+  }
+  a.fmt = in_dtype == LB_BF16 ? 1 : 0;
+  // rows per CTA: keep >= ~2 CTAs per SM, but fold slabs together when the grid would be far
+  // larger (fewer global atomics per output element)
+  const int slabs_total = (a.M + WG_ROWS - 1) / WG_ROWS;
+  int slabs = 1;
+  while (slabs < 8 && static_cast<long long>(nblk) * ((slabs_total + 2 * slabs - 1) / (2 * slabs)) >= 296) slabs *= 2;
+  a.slabs = slabs;
+  dim3 grid(nblk, (slabs_total + slabs - 1) / slabs);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch ((a.r + 3) / 4) {
+    case 1: wgrad_kernel<1><<<grid, WG_WARPS * 32, 0, st>>>(a); break;
+    case 2: wgrad_kernel<2><<<grid, WG_WARPS * 32, 0, st>>>(a); break;
+    case 3: wgrad_kernel<3><<<grid, WG_WARPS * 32, 0, st>>>(a); break;
+    default: wgrad_kernel<4><<<grid, WG_WARPS * 32, 0, st>>>(a); break;
+  }
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
 static int wgrad_launch(const void* S, const float* V, const float* diag, float scale, float* out,
                         long long out_js, long long out_cs, int M, int C, int r, int H, int W,
                         int dy, int dx, float drop_p, const void* seed_dev, int in_dtype,
                         void* stream) {
   if (H < 0 || W < 0 || (H > 0) != (W > 0)) return LB_ERR_SHAPE;
   if (H > 0 && (M % (H * W)) != 0) return LB_ERR_SHAPE;
-  if (M <= 0 || C <= 0 || (C % 8) != 0) return LB_ERR_SHAPE;
-  if (r < 1 || r > 16) return LB_ERR_RANK;
-  if (in_dtype != LB_BF16 && in_dtype != LB_F16) return LB_ERR_DTYPE;
-  if ((reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(V)) & 15) return LB_ERR_ALIGN;
-  const int fmt = in_dtype == LB_BF16 ? 1 : 0;
-  dim3 grid((C + WG_COLS - 1) / WG_COLS, (M + WG_ROWS - 1) / WG_ROWS);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const uint2* S32 = reinterpret_cast<const uint2*>(S);
-  switch ((r + 3) / 4) {
-    case 1: wgrad_kernel<1><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt, H, W, dy, dx, drop_p, reinterpret_cast<const unsigned long long*>(seed_dev)); break;
-    case 2: wgrad_kernel<2><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt, H, W, dy, dx, drop_p, reinterpret_cast<const unsigned long long*>(seed_dev)); break;
-    case 3: wgrad_kernel<3><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt, H, W, dy, dx, drop_p, reinterpret_cast<const unsigned long long*>(seed_dev)); break;
-    default: wgrad_kernel<4><<<grid, WG_WARPS * 32, 0, st>>>(S32, V, diag, scale, out, out_js, out_cs, M, C, r, fmt, H, W, dy, dx, drop_p, reinterpret_cast<const unsigned long long*>(seed_dev)); break;
-  }
-  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+  WgArgs a = {};
+  a.pr[0].S = reinterpret_cast<const uint2*>(S); a.pr[0].V = V; a.pr[0].out = out;
+  a.pr[0].js = out_js; a.pr[0].cs = out_cs; a.pr[0].C = C; a.pr[0].drop_p = drop_p;
+  a.pr[1].C = 0;
+  a.diag = diag; a.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
+  a.scale = scale; a.M = M; a.r = r; a.cH = H; a.cW = W; a.dy = dy; a.dx = dx;
+  return wgrad_run(a, in_dtype, stream);
+}
+
+extern "C" int lb_lora_wgrad_pair(const void* X, const float* dTs, float* dA, long long dA_js,
+                                  long long dA_cs, int K, const void* gY, const float* T, float* dB,
+                                  long long dB_js, long long dB_cs, int N, const float* diag,
+                                  float scale, int M, int r, float drop_p, const void* seed_dev,
+                                  int in_dtype, void* stream) {
+  if (!(drop_p >= 0.f && drop_p < 1.f) || (drop_p > 0.f && seed_dev == nullptr)) return LB_ERR_SHAPE;
+  WgArgs a = {};
+  a.pr[0].S = reinterpret_cast<const uint2*>(X); a.pr[0].V = dTs; a.pr[0].out = dA;
+  a.pr[0].js = dA_js; a.pr[0].cs = dA_cs; a.pr[0].C = K; a.pr[0].drop_p = 0.f;
+  a.pr[1].S = reinterpret_cast<const uint2*>(gY); a.pr[1].V = T; a.pr[1].out = dB;
+  a.pr[1].js = dB_js; a.pr[1].cs = dB_cs; a.pr[1].C = N; a.pr[1].drop_p = drop_p;
+  a.diag = diag; a.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
+  a.scale = scale; a.M = M; a.r = r;
+  return wgrad_run(a, in_dtype, stream);
 }
 
 extern "C" int lb_lora_up_dropout(void* Y, int y_dtype, const float* T, const float* up,

@@ -186,16 +186,20 @@ class _FusedLoraLinearFn(torch.autograd.Function):
         need_x, need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         sink = st.grad_sink
         dA = dB = None
+        tA = tB = None
         if need_a:
-            tgt = sink[0] if sink is not None else torch.zeros((r, K), device=gy.device, dtype=torch.float32)
-            ops.wgrad(x2d, dTs, ctx.diag, ctx.scale, tgt, K, 1, r)
-            if sink is None:
-                dA = tgt.to(A.dtype).view_as(A)
+            tA = sink[0] if sink is not None else torch.zeros((r, K), device=gy.device, dtype=torch.float32)
         if need_b:
-            tgt = sink[1] if sink is not None else torch.zeros((N, r), device=gy.device, dtype=torch.float32)
-            ops.wgrad(gy2d, T, ctx.diag, ctx.scale, tgt, 1, r, r)
-            if sink is None:
-                dB = tgt.to(B.dtype).view_as(B)
+            tB = sink[1] if sink is not None else torch.zeros((N, r), device=gy.device, dtype=torch.float32)
+        if need_a and need_b:
+            ops.wgrad_pair(x2d, dTs, tA, gy2d, T, tB, ctx.diag, ctx.scale, r)
+        elif need_a:
+            ops.wgrad(x2d, dTs, ctx.diag, ctx.scale, tA, K, 1, r)
+        elif need_b:
+            ops.wgrad(gy2d, T, ctx.diag, ctx.scale, tB, 1, r, r)
+        if sink is None:
+            dA = tA.to(A.dtype).view_as(A) if need_a else None
+            dB = tB.to(B.dtype).view_as(B) if need_b else None
         dx = dX.view(ctx.x_shape).to(ctx.x_dtype) if need_x else None
         return dx, dA, dB, None
 

@@ -198,3 +198,17 @@ def wgrad_masked(S: torch.Tensor, V: torch.Tensor, diag, scale: float, out: torc
                                       out_cs, M, C, r, float(p), ptr(seed), dtype_code(S.dtype),
                                       stream_ptr()), "lb_lora_wgrad_masked")
     _count()
+
+
+def wgrad_pair(x2d: torch.Tensor, dTs: torch.Tensor, dA: torch.Tensor, gy2d: torch.Tensor,
+               T: torch.Tensor, dB: torch.Tensor, diag, scale: float, r: int, p: float = 0.0,
+               seed: Optional[torch.Tensor] = None):
+    """dA [r,K] += s*d * dTs^T x2d  and  dB [N,r] += s*d * (mask o gy2d)^T T  in one launch."""
+    _req_cuda(x2d, dTs, dA, gy2d, T, dB)
+    M, K = x2d.shape
+    N = gy2d.shape[1]
+    assert gy2d.shape[0] == M and dA.dtype == torch.float32 and dB.dtype == torch.float32
+    check(_C.lib.lb_lora_wgrad_pair(ptr(x2d), ptr(dTs), ptr(dA), K, 1, K, ptr(gy2d), ptr(T), ptr(dB),
+                                    1, r, N, ptr(diag), float(scale), M, r, float(p), ptr(seed),
+                                    dtype_code(x2d.dtype), stream_ptr()), "lb_lora_wgrad_pair")
+    _count()

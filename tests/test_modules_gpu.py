@@ -258,3 +258,60 @@ def test_training_step_cuda_graph_equals_eager():
     assert int(tr.arena.step_dev) == 5
     # both paths train: the loss on the fixed sample/noise distribution stays in a sane range
     assert max(losses[0] + losses[1]) < 10.0
+
+
+def test_extended_training_step_matches_reference_step_tiny():
+    """--use_extended_lora shape of the step (Linear + ResnetBlock2D Conv2d sites through the arena:
+    conv dA/dB land in the flat gradient buffer) vs the oracle's reference step. Dropout is set
+    to 0 on both sides here (mask streams differ by design; tests/test_dropout_gpu.py)."""
+    import lora_b200 as L
+    from lora_b200.host.ddpm import DDPMNoiser
+    from lora_b200.train import LoraTrainStep, StepConfig
+    from oracle.ref_modules import ref_inject
+    from oracle.ref_step import RefDreamboothStep
+
+    unet, text = _tiny_models(seed=2)
+    unet = unet.to(memory_format=torch.channels_last)
+    unet_r, text_r = copy.deepcopy(unet), copy.deepcopy(text)
+    L.inject_trainable_lora_extended(unet, r=4)
+    L.inject_trainable_lora(text, target_replace_module={"CLIPAttention"}, r=4)
+    us = ref_inject(unet_r, {"ResnetBlock2D", "CrossAttention", "Attention", "GEGLU"}, r=4, extended=True)
+    ts = ref_inject(text_r, {"CLIPAttention"}, r=4)
+    ours = [m for m in list(unet.modules()) + list(text.modules()) if type(m).__name__.startswith("LoraInjected")]
+    assert len(ours) == len(us) + len(ts)
+    assert any(type(m).__name__ == "LoraInjectedConv2d" for m in ours)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    for o, r in zip(ours, us + ts):
+        o.dropout.p = 0.0
+        r.p = 0.0
+        o.lora_up.weight.data.normal_(0, 0.05, generator=g)
+        r.up.data.copy_(o.lora_up.weight.data)
+        r.down.data.copy_(o.lora_down.weight.data)
+    cfg = StepConfig(use_cuda_graph=False, autocast_dtype=torch.bfloat16)
+    tr = LoraTrainStep(unet, text, cfg, latent_shape=(1, 4, 16, 16), seq_len=77, device=DEV)
+    ref = RefDreamboothStep(unet_r, text_r, DDPMNoiser(device=DEV), us, ts, autocast_dtype=torch.bfloat16)
+    lat = torch.randn(1, 4, 16, 16, device=DEV) * 0.18215
+    ids = torch.randint(0, 1000, (1, 77), device=DEV)
+    tr.latents.copy_(lat)
+    tr.input_ids.copy_(ids)
+    # gradients of the first step, identical noise / timestep
+    torch.manual_seed(21)
+    noise = torch.randn_like(lat)
+    t = torch.randint(0, 1000, (1,), device=DEV).long()
+    ref.forward_loss(lat, ids, noise, t).backward()
+    g_ref = torch.cat([p.grad.flatten() for p in ref.unet_params + ref.text_params])
+    ref.opt.zero_grad()
+    noisy = tr.noiser.add_noise(lat, noise, t).contiguous(memory_format=torch.channels_last)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        pred = unet(noisy, t, text(ids)[0]).sample
+    torch.nn.functional.mse_loss(pred.float(), noise.float()).backward()
+    g_ours = torch.cat([p.grad.flatten() for p in tr.arena.parameters()])
+    assert g_ours.numel() == g_ref.numel()
+    assert rel(g_ours, g_ref) < 3e-2
+    tr.arena.zero_grad()
+    for step in range(2):
+        torch.manual_seed(300 + step)
+        l_ref = float(ref.step(lat, ids))
+        torch.manual_seed(300 + step)
+        l_ours = float(tr.step_device())
+        assert abs(l_ours - l_ref) < 1e-2 * abs(l_ref), (step, l_ours, l_ref)
