@@ -59,6 +59,9 @@ int lb_lora_linear_fwd(const void* X, const void* W, const float* bias, const vo
 /* Benchmark/profiling knob: tile schedule of lb_lora_linear_fwd. 0 = auto (default),
  * 1 = one tile per CTA, 2 = persistent CTAs with double-buffered TMEM accumulators. */
 int lb_debug_set_linear_mode(int mode);
+/* Profiling knob: device buffer (16 x uint64) receiving %globaltimer phase stamps of CTA (0,0) of
+ * subsequent lb_lora_linear_fwd launches; NULL switches it off. */
+int lb_debug_set_stamp_buffer(void* dev_buf);
 
 /* Skinny weight-gradient reduction (streams S once, fp32 atomics into out):
  *     out[j*out_js + c*out_cs] += scale * diag[j] * sum_m V[m,j] * S[m,c]     j < r, c < C

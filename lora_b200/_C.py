@@ -40,6 +40,7 @@ def _load():
                                 f32, f32, f32, vp, vp, vp, vp], i32),
         "lb_refresh_shadows": ([vp, vp, i32, i32, vp, i32, vp], i32),
         "lb_debug_set_linear_mode": ([i32], i32),
+        "lb_debug_set_stamp_buffer": ([vp], i32),
         "lb_lora_wgrad_pair": ([vp, vp, vp, ll, ll, i32, vp, vp, vp, ll, ll, i32, vp, f32, i32, i32,
                                 f32, vp, i32, vp], i32),
         "lb_svd_mul": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, vp], i32),

@@ -51,7 +51,15 @@ struct FusedParams {
   int kh, kw, pad_h, pad_w;
   int TH, TW, tiles_h, tiles_w;
   int down_per_tap;    // 1: D columns advance with the tap (forward); 0: D restarts every tap (dX)
+  unsigned long long* dbg;  // profiling only: 16 x %globaltimer stamps written by CTA (0,0), or null
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define LB_STAMP(i) do { if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[i] = gtimer(); } while (0)
 
 template <int BLOCK_N, int STAGES, typename OutT, int G>
 struct Smem {
@@ -94,6 +102,7 @@ fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) LB_STAMP(0);   // kernel entry
   const int n_blk = blockIdx.x, m_blk = blockIdx.y;
   const int n0 = n_blk * BLOCK_N;
   // row-tile origin
@@ -131,18 +140,25 @@ fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     mbar_init(bar_final, 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
-    tmem_alloc(sbase + S::OFF_TMEM, S::TMEM_COLS);
-    tmem_relinquish();
+  __syncthreads();  // barriers initialised
+  // The TMA producer starts streaming right away; TMEM allocation (a few hundred cycles) proceeds
+  // concurrently in warp 1 and is published to the MMA/epilogue warps through named barrier 2.
+  uint32_t tmem = 0;
+  if (warp != 0) {
+    if (warp == 1) {
+      tmem_alloc(sbase + S::OFF_TMEM, S::TMEM_COLS);
+      tmem_relinquish();
+    }
+    tc_fence_before();
+    named_bar_sync(2, NUM_THREADS - 32);
+    tc_fence_after();
+    tmem = *tmem_slot;
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      LB_STAMP(1);                       // first TMA about to be issued
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -174,6 +190,7 @@ fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(bar_full(s), ph);
+        if (kb == 0) LB_STAMP(2);          // first stage landed
         tc_fence_after();
         const uint32_t sa = sbase + s * S::STAGE_BYTES;
         const uint32_t sb = sa + S::A_BYTES;
@@ -195,8 +212,10 @@ fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         umma_commit(bar_empty(s));  // frees the smem slot when these MMAs retire
       }
       umma_commit(bar_acc);
+      LB_STAMP(3);                         // all main-loop MMAs issued
       // LoRA up-projection(s): acc[:, 0:BLOCK_N] += T'_g[128,16] . U_g[BLOCK_N,16]^T
       mbar_wait(bar_tready, 0);
+      LB_STAMP(5);                         // T' operand visible to the MMA warp
       tc_fence_after();
 #pragma unroll
       for (int g = 0; g < G; ++g) {
@@ -249,6 +268,7 @@ fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
     // T group(s) out of TMEM -> (optional) global save -> scaled 16-bit operand(s) in smem
     mbar_wait(bar_acc, 0);
+    if (et == 0) LB_STAMP(4);            // main-loop MMAs completed (accumulator ready)
     tc_fence_after();
 #pragma unroll
     for (int g = 0; g < G; ++g) {
@@ -299,6 +319,7 @@ fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
     // Final accumulator -> (+bias) -> OutT -> swizzled staging -> TMA store
     mbar_wait(bar_final, 0);
+    if (et == 0) LB_STAMP(6);            // LoRA MMA completed
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -342,8 +363,10 @@ fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         else
           tma_store_2d(&tmY, sbase + S::OFF_OUT + b * S::BOX_BYTES, col, m0);
       }
+      LB_STAMP(7);                       // drain done, stores issued
       tma_store_commit();
       tma_store_wait_read0();
+      LB_STAMP(8);                       // staging buffer released
     }
   }
 
@@ -352,6 +375,7 @@ fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem, S::TMEM_COLS);
   }
+  if (threadIdx.x == 32) LB_STAMP(9);    // kernel exit
 }
 
 }  // namespace lb

@@ -61,7 +61,8 @@ static int launch_persistent(const void* X, const void* W, const void* Dn, void*
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }
 
-static int g_linear_mode = 0;  // 0 = auto, 1 = one tile per CTA (2-3 CTAs/SM), 2 = persistent
+static int g_linear_mode = 0;
+static unsigned long long* g_dbg = nullptr;  // profiling: device buffer of 16 timestamps  // 0 = auto, 1 = one tile per CTA (2-3 CTAs/SM), 2 = persistent
 
 }  // namespace lb
 
@@ -69,6 +70,14 @@ static int g_linear_mode = 0;  // 0 = auto, 1 = one tile per CTA (2-3 CTAs/SM), 
 extern "C" int lb_debug_set_linear_mode(int mode) {
   if (mode < 0 || mode > 11) return LB_ERR_SHAPE;   // schedule + 4 * block_n choice (0 auto, 1: 64, 2: 128)
   lb::g_linear_mode = mode;
+  return LB_OK;
+}
+
+// Profiling knob: CTA (0,0) of the next lb_lora_linear_fwd launches writes %globaltimer stamps
+// (entry, first TMA, first stage landed, MMAs issued, accumulator ready, T' ready, LoRA MMA done,
+// stores issued, staging released, exit) into this device buffer of 16 uint64 (NULL: off).
+extern "C" int lb_debug_set_stamp_buffer(void* dev_buf) {
+  lb::g_dbg = reinterpret_cast<unsigned long long*>(dev_buf);
   return LB_OK;
 }
 
@@ -93,12 +102,13 @@ extern "C" int lb_lora_linear_fwd(const void* X, const void* W, const float* bia
   FusedParams p = {};
   p.bias = bias; p.up = up; p.up_rs = up_rs; p.up_cs = up_cs; p.up_gs = 0; p.diag = diag;
   p.t_out = T_out; p.t_in = T_in; p.scale = scale; p.M = M; p.N = N; p.K = K; p.r = r;
-  p.fmt = (in_dtype == LB_BF16) ? 1 : 0; p.t_group = 0;
+  p.fmt = (in_dtype == LB_BF16) ? 1 : 0; p.t_group = 0; p.dbg = g_dbg;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   const int sched = g_linear_mode & 3, bn_choice = g_linear_mode >> 2;
   const long long tiles128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
   bool narrow = tiles128 < 120;  // not enough 128-wide tiles to fill 148 SMs: halve BLOCK_N
+  if (K >= 2048 && tiles128 >= 64) narrow = false;  // long K: per-tile work is large, keep W reuse
   if (bn_choice == 1) narrow = true;
   if (bn_choice == 2) narrow = false;
   // More tiles than SMs: persistent CTAs with a double-buffered TMEM accumulator (epilogue of

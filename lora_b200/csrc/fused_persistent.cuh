@@ -84,14 +84,20 @@ fused_lora_persistent_kernel(const __grid_constant__ CUtensorMap tmX,
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
-    tmem_alloc(sbase + S::OFF_TMEM, S::TMEM_COLS);
-    tmem_relinquish();
+  __syncthreads();  // barriers initialised
+  // The TMA producer starts streaming right away; TMEM allocation (a few hundred cycles) proceeds
+  // concurrently in warp 1 and is published to the MMA/epilogue warps through named barrier 2.
+  uint32_t tmem = 0;
+  if (warp != 0) {
+    if (warp == 1) {
+      tmem_alloc(sbase + S::OFF_TMEM, S::TMEM_COLS);
+      tmem_relinquish();
+    }
+    tc_fence_before();
+    named_bar_sync(2, NUM_THREADS - 32);
+    tc_fence_after();
+    tmem = *tmem_slot;
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer

@@ -235,8 +235,11 @@ apply_kernel(const float* __restrict__ Y, const float* __restrict__ Mx, const fl
 #pragma unroll
     for (int i = 0; i < L; ++i) s += v[i] * Ms[i][j];
     if (scale_mode != 0) {
+      // colscale is sorted descending (lb_svd_jacobi): entry 0 is the largest singular value.
+      // Directions below 1e-6 of it are numerically null: dropped (zero column) instead of divided.
       const float c = colscale[static_cast<size_t>(b) * L + j];
-      s = (scale_mode == 1) ? s * c : (c > 0.f ? s / c : 0.f);
+      const float cmax = colscale[static_cast<size_t>(b) * L];
+      s = (scale_mode == 1) ? s * c : ((c > 1e-6f * cmax && c > 0.f) ? s / c : 0.f);
     }
     if (transposed) o[static_cast<size_t>(j) * out_pitch + row] = s;
     else o[static_cast<size_t>(row) * out_pitch + j] = s;

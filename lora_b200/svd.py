@@ -7,7 +7,7 @@ singular triplets, up = U_r diag(S_r), down = Vh_r, clamp both symmetrically at 
 
 The reference loops over sites calling a full `torch.linalg.svd`. Here all same-shape sites are
 processed together by the primitives in csrc/svd.cu (randomized range finder, 32 probes,
-q power iterations with CholeskyQR2, 32x32 Jacobi): the only passes over the weights are
+q power iterations re-orthonormalised through a 32x32 Jacobi eigen-solve): the only passes over the weights are
 2(q+1) streaming reads of (W_tuned, W_base).
 
 Singular vectors are unique up to a per-component sign, and the reference's clamp threshold is a
@@ -32,13 +32,17 @@ def _ptr_array(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
     return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=device)
 
 
-def _orth2(Y: torch.Tensor, G: torch.Tensor, Rinv: torch.Tensor, rows: int, batch: int):
-    """CholeskyQR2 in place: Y <- orthonormal basis of span(Y)."""
+def _orth2(Y: torch.Tensor, G: torch.Tensor, V: torch.Tensor, sig: torch.Tensor, rows: int, batch: int,
+           sweeps: int = 8):
+    """Orthonormalise the 32 columns of Y in place, twice (like CholeskyQR2, but rank-revealing):
+    G = Y^T Y = V diag(s^2) V^T (Jacobi)  ->  Y <- Y V diag(1/s), numerically null directions
+    (s < 1e-6 s_max) become zero columns. A Cholesky factor would break down exactly there, and
+    exactly-low-rank deltas are a real input (a fine-tune that IS a merged LoRA)."""
     lib, st = _C.lib, stream_ptr()
     for _ in range(2):
         check(lib.lb_svd_gram(ptr(Y), ptr(G), rows, batch, st), "lb_svd_gram")
-        check(lib.lb_svd_chol_inv(ptr(G), ptr(Rinv), batch, st), "lb_svd_chol_inv")
-        check(lib.lb_svd_apply(ptr(Y), ptr(Rinv), None, 0, ptr(Y), rows, L, L, 0, rows * L, batch, st),
+        check(lib.lb_svd_jacobi(ptr(G), ptr(V), ptr(sig), batch, sweeps, st), "lb_svd_jacobi")
+        check(lib.lb_svd_apply(ptr(Y), ptr(V), ptr(sig), 2, ptr(Y), rows, L, L, 0, rows * L, batch, st),
               "lb_svd_apply")
         ops._count(3)
 
@@ -66,19 +70,18 @@ def svd_lowrank_batched(W_tuned: Sequence[torch.Tensor], W_base: Sequence[torch.
     Z = torch.empty((batch, K, L), **f32)
     Y = torch.empty((batch, N, L), **f32)
     G = torch.empty((batch, L, L), **f32)
-    Rinv = torch.empty((batch, L, L), **f32)
     V = torch.empty((batch, L, L), **f32)
     sigma = torch.empty((batch, L), **f32)
 
     check(lib.lb_svd_randn(ptr(Z), Z.numel(), ctypes.c_ulonglong(seed * 2654435761 + 12345), st), "lb_svd_randn")
     check(lib.lb_svd_mul(ptr(pt), ptr(pb), wdt, ptr(Z), ptr(Y), N, K, batch, 0, st), "lb_svd_mul")
     ops._count(2)
-    _orth2(Y, G, Rinv, N, batch)
+    _orth2(Y, G, V, sigma, N, batch)
     for _ in range(power_iters):
         check(lib.lb_svd_mul(ptr(pt), ptr(pb), wdt, ptr(Y), ptr(Z), N, K, batch, 1, st), "lb_svd_mul")
-        _orth2(Z, G, Rinv, K, batch)
+        _orth2(Z, G, V, sigma, K, batch)
         check(lib.lb_svd_mul(ptr(pt), ptr(pb), wdt, ptr(Z), ptr(Y), N, K, batch, 0, st), "lb_svd_mul")
-        _orth2(Y, G, Rinv, N, batch)
+        _orth2(Y, G, V, sigma, N, batch)
         ops._count(2)
     # Q = Y (orthonormal); Z = dW^T Q = B^T ;  B B^T = Z^T Z = Uh diag(s^2) Uh^T
     check(lib.lb_svd_mul(ptr(pt), ptr(pb), wdt, ptr(Y), ptr(Z), N, K, batch, 1, st), "lb_svd_mul")

@@ -1,6 +1,7 @@
 """Launch the fused LoRA-linear kernel on representative SD1.5 site shapes (for ncu --set full)
 and print CUDA-event timings per shape and tile schedule (algorithmic GB/s, TFLOP/s).
 L2 is flushed (256 MB write) between timed launches."""
+import ctypes
 import json
 import os
 import sys
@@ -78,3 +79,37 @@ for (M, C, r) in [(4096, 320, 4), (4096, 2560, 4), (1024, 640, 4), (256, 10240, 
 
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/site_times.json", "w"), indent=1)
+
+# ---- phase breakdown of one CTA (globaltimer stamps inside the one-tile-per-CTA kernel)
+names = ["entry", "first TMA issue", "first stage landed", "MMAs issued", "acc ready", "T' ready",
+         "LoRA MMA done", "stores issued", "staging released", "exit"]
+stamps = torch.zeros(16, device=dev, dtype=torch.int64)
+phase = []
+for (M, K, N, r) in [(77, 768, 768, 4), (256, 1280, 1280, 4), (1024, 640, 640, 4), (4096, 320, 320, 4)]:
+    x = torch.randn(M, K, device=dev, dtype=dt)
+    w = torch.randn(N, K, device=dev, dtype=dt) * 0.02
+    a = torch.randn(r, K, device=dev)
+    b = torch.randn(N, r, device=dev) * 0.01
+    d16 = ops.cast_rows_pad16(a, K, 1, r, K, dt)
+    _C.lib.lb_debug_set_linear_mode(1)           # one tile per CTA (stamps live in that kernel)
+    for cold in (True, False):
+        ops.fused_linear(x, w, None, d16, b, r, 1, None, 1.0, r, dt, True)
+        if cold:
+            flush.zero_()
+        torch.cuda.synchronize()
+        stamps.zero_()
+        _C.lib.lb_debug_set_stamp_buffer(ctypes.c_void_p(stamps.data_ptr()))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.fused_linear(x, w, None, d16, b, r, 1, None, 1.0, r, dt, True)
+        e1.record()
+        torch.cuda.synchronize()
+        _C.lib.lb_debug_set_stamp_buffer(None)
+        t = stamps.cpu().tolist()
+        rel = {names[i]: (t[i] - t[0]) for i in range(10) if t[i]}
+        row = {"mode": "phases_ns", "M": M, "K": K, "N": N, "cold_L2": cold,
+               "event_us": round(e0.elapsed_time(e1) * 1e3, 2), **rel}
+        phase.append(row)
+        print(row, flush=True)
+_C.lib.lb_debug_set_linear_mode(0)
+json.dump(rows + phase, open("gpurun_out/site_times.json", "w"), indent=1)

@@ -35,7 +35,9 @@ def make_pairs(N, K, batch, true_rank=8, dtype=torch.float16, seed=0):
                                             (96, 200, 2, 1)])
 def test_batched_svd_matches_exact_svd(N, K, batch, rank):
     from lora_b200.svd import svd_lowrank_batched
-    Wb, Wt = make_pairs(N, K, batch, seed=N + K)
+    # the planted spectrum must be at least as wide as the requested rank (below it, singular
+    # vectors of the isotropic noise floor are not unique)
+    Wb, Wt = make_pairs(N, K, batch, true_rank=max(8, rank), seed=N + K)
     up, down, sigma = svd_lowrank_batched([w.to(DEV) for w in Wt], [w.to(DEV) for w in Wb], rank)
     torch.cuda.synchronize()
     for b in range(batch):
@@ -51,6 +53,21 @@ def test_batched_svd_matches_exact_svd(N, K, batch, rank):
         assert float(got) <= float(opt) * 1.001 + 1e-12
         gram = down[b].double().cpu() @ down[b].double().cpu().T
         assert rel(gram, torch.eye(rank, dtype=torch.float64)) < 2e-3
+
+
+def test_exactly_low_rank_delta_is_handled():
+    """dW of exact rank 3 (a merged LoRA), asked for rank 8: the 5 surplus triplets are zero, no NaN."""
+    from lora_b200.svd import svd_lowrank_batched
+    g = torch.Generator().manual_seed(0)
+    base = (torch.randn(640, 320, generator=g) * 0.05)
+    low = torch.randn(640, 3, generator=g) @ torch.randn(3, 320, generator=g) * 0.01
+    up, down, sigma = svd_lowrank_batched([(base + low).to(DEV)], [base.to(DEV)], 8)
+    torch.cuda.synchronize()
+    assert torch.isfinite(up).all() and torch.isfinite(down).all() and torch.isfinite(sigma).all()
+    S = torch.linalg.svdvals(low.double())
+    assert rel(sigma[0, :3], S[:3]) < 1e-3
+    assert float(sigma[0, 3:8].max()) < 1e-4 * float(S[0])
+    assert rel(up[0].double().cpu() @ down[0].double().cpu(), low) < 1e-3
 
 
 def test_overwrite_base_matches_oracle_on_tiny_models():
