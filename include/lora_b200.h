@@ -65,6 +65,7 @@ int lb_debug_set_stamp_buffer(void* dev_buf);
 
 /* Skinny weight-gradient reduction (streams S once, fp32 atomics into out):
  *     out[j*out_js + c*out_cs] += scale * diag[j] * sum_m V[m,j] * S[m,c]     j < r, c < C
+ * S may also be fp32 (in_dtype = LB_F32; the fp32-faithful mode keeps X and gY in fp32).
  * dA[r,K]: S = X[M,K],  V = gY.B (T_out of the dX call), out_js = K, out_cs = 1
  * dB[N,r]: S = gY[M,N], V = X.A^T (T_out of the forward), out_js = 1, out_cs = r
  * Replaces the autograd-generated dA/dB GEMMs of lora.py:53-58 (W frozen: no dW).
@@ -142,6 +143,13 @@ int lb_cast_conv_weight(const void* src, int src_dtype, void* dst16, void* dstT1
  * A[r,K] -> down16:  src_rs = K, src_cs = 1.    B[N,r] -> B^T padded: src_rs = 1, src_cs = r. */
 int lb_cast_rows_pad16(const float* src, long long src_rs, long long src_cs, void* dst16, int r,
                        int C, int out_dtype, void* stream);
+
+/* fp32-faithful mode ("split-bf16"): dst16 [R, 3C] bf16 = three bf16 terms of src [R,C] fp32 side
+ * by side along K; pattern 0 (activations) [hi|lo|hi], pattern 1 (weights, factors) [hi|hi|lo], so
+ * an ordinary K-major bf16 GEMM over 3C columns evaluates hi*hi + lo*hi + hi*lo (error 2^-16).
+ * The fused kernels are then called with K := 3K; nothing else changes. */
+int lb_split_bf16x3(const float* src, long long src_rs, void* dst16, int R, int C, int pattern,
+                    void* stream);
 
 /* Frozen-weight preparation: src [R,C] (LB_F32/LB_BF16/LB_F16) -> dst16 [R,C] and/or
  * dstT16 [C,R] (either may be NULL). One-time cost per frozen weight. */

@@ -4,4 +4,6 @@ from .lora import *  # noqa: F401,F403
 from .lora import (_find_children, _find_modules, _find_modules_v2, _text_lora_path,  # noqa: F401
                    _ti_lora_path)
 
+from .modules import get_fp32_mode, set_fp32_mode  # noqa: F401,E402
+
 __version__ = "0.1.0"

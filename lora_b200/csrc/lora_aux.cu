@@ -87,7 +87,8 @@ wgrad_kernel(const WgArgs a) {
   const int C = P.C;
   const int c0 = cblk * WG_COLS + lane * 4;
   const bool col_ok = c0 < C;                          // C % 8 == 0 => whole 4-column group valid
-  const size_t pitch = static_cast<size_t>(C) >> 2;    // row pitch in 8-byte words
+  const bool f32in = a.fmt == 2;                       // fp32 rows: 16 bytes per lane
+  const size_t pitch = static_cast<size_t>(C) >> 2;    // row pitch in 8-byte words (16-bit rows)
   const int cH = which ? 0 : a.cH;
   for (int i = threadIdx.x; i < RQ * 4 * WG_COLS; i += WG_WARPS * 32) (&red[0][0])[i] = 0.f;
   __syncthreads();
@@ -99,7 +100,7 @@ wgrad_kernel(const WgArgs a) {
   const unsigned long long sd = (drop_p > 0.f) ? a.seed_dev[0] : 0ull;
   const float inv = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
 
-  auto load_rows = [&](int m_base, uint2 (&raw)[WG_RPW]) {
+  auto load_rows = [&](int m_base, uint4 (&raw)[WG_RPW]) {
 #pragma unroll
     for (int i = 0; i < WG_RPW; ++i) {
       const int m = m_base + i;
@@ -112,12 +113,19 @@ wgrad_kernel(const WgArgs a) {
         ok = hh >= 0 && hh < cH && ww >= 0 && ww < a.cW;
         src = static_cast<long long>(m) + a.dy * a.cW + a.dx;
       }
-      raw[i] = ok ? __ldg(P.S + static_cast<size_t>(src) * pitch + (c0 >> 2)) : make_uint2(0u, 0u);
+      if (!ok) {
+        raw[i] = make_uint4(0u, 0u, 0u, 0u);
+      } else if (f32in) {
+        raw[i] = __ldg(reinterpret_cast<const uint4*>(P.S) + static_cast<size_t>(src) * pitch + (c0 >> 2));
+      } else {
+        const uint2 v = __ldg(P.S + static_cast<size_t>(src) * pitch + (c0 >> 2));
+        raw[i] = make_uint4(v.x, v.y, 0u, 0u);
+      }
     }
   };
 
   const int m_first = blockIdx.y * a.slabs * WG_ROWS + warp * WG_RPW;
-  uint2 cur[WG_RPW], nxt[WG_RPW];
+  uint4 cur[WG_RPW], nxt[WG_RPW];
   load_rows(m_first, cur);
   for (int sl = 0; sl < a.slabs; ++sl) {
     const int m_base = m_first + sl * WG_ROWS;
@@ -127,8 +135,14 @@ wgrad_kernel(const WgArgs a) {
     for (int i = 0; i < WG_RPW; ++i) {
       const int m = m_base + i;
       if (m < a.M) {
-        float2 lo = ld16x2(cur[i].x, a.fmt), hi = ld16x2(cur[i].y, a.fmt);
-        float x[4] = {lo.x, lo.y, hi.x, hi.y};
+        float x[4];
+        if (f32in) {
+          x[0] = __uint_as_float(cur[i].x); x[1] = __uint_as_float(cur[i].y);
+          x[2] = __uint_as_float(cur[i].z); x[3] = __uint_as_float(cur[i].w);
+        } else {
+          const float2 lo = ld16x2(cur[i].x, a.fmt), hi = ld16x2(cur[i].y, a.fmt);
+          x[0] = lo.x; x[1] = lo.y; x[2] = hi.x; x[3] = hi.y;
+        }
         if (drop_p > 0.f) {  // S = gY of a dropout site: the branch saw mask/(1-p)
           const unsigned long long e = static_cast<unsigned long long>(m) * C + c0;
 #pragma unroll
@@ -297,6 +311,25 @@ __global__ void cast_weight_kernel(const SrcT* __restrict__ src, int src_fmt,
   }
 }
 
+// fp32 -> three bf16 terms laid side by side along K ("split-bf16" operands for the fp32-faithful
+// mode): x = hi + lo + O(2^-16 |x|), hi = bf16(x), lo = bf16(x - hi).
+//   pattern 0 (activation side): [hi | lo | hi]      pattern 1 (weight side): [hi | hi | lo]
+// so that  sum_k a3[k] w3[k] = a_hi w_hi + a_lo w_hi + a_hi w_lo  (the dropped lo*lo term is 2^-16).
+__global__ void split_bf16x3_kernel(const float* __restrict__ src, long long src_rs,
+                                    uint16_t* __restrict__ dst, int R, int C, int pattern) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;
+  if (c >= C) return;
+  const float x = src[r * src_rs + c];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+  const uint16_t h = *reinterpret_cast<const uint16_t*>(&hi), l = *reinterpret_cast<const uint16_t*>(&lo);
+  uint16_t* row = dst + static_cast<size_t>(r) * 3 * C;
+  row[c] = h;
+  row[C + c] = pattern == 0 ? l : h;
+  row[2 * C + c] = pattern == 0 ? h : l;
+}
+
 // frozen conv weight [Cout,Cin,T] -> forward operand [Cout, T*Cin] and flipped-transposed
 // input-gradient operand [Cin, T*Cout]; one-time per frozen weight, one thread per element
 template <typename SrcT>
@@ -456,7 +489,7 @@ extern "C" int lb_lora_wgrad_masked(const void* S, const float* V, const float* 
 static int wgrad_run(WgArgs& a, int in_dtype, void* stream) {
   if (a.M <= 0) return LB_ERR_SHAPE;
   if (a.r < 1 || a.r > 16) return LB_ERR_RANK;
-  if (in_dtype != LB_BF16 && in_dtype != LB_F16) return LB_ERR_DTYPE;
+  if (in_dtype != LB_BF16 && in_dtype != LB_F16 && in_dtype != LB_F32) return LB_ERR_DTYPE;
   int nblk = 0;
   for (int i = 0; i < 2; ++i) {
     const WgProblem& P = a.pr[i];
@@ -465,7 +498,7 @@ static int wgrad_run(WgArgs& a, int in_dtype, void* stream) {
     if ((reinterpret_cast<uintptr_t>(P.S) | reinterpret_cast<uintptr_t>(P.V)) & 15) return LB_ERR_ALIGN;
     nblk += (P.C + WG_COLS - 1) / WG_COLS;
   }
-  a.fmt = in_dtype == LB_BF16 ? 1 : 0;
+  a.fmt = in_dtype == LB_BF16 ? 1 : (in_dtype == LB_F32 ? 2 : 0);
   // rows per CTA: keep >= ~2 CTAs per SM, but fold slabs together when the grid would be far
   // larger (fewer global atomics per output element)
   const int slabs_total = (a.M + WG_ROWS - 1) / WG_ROWS;
@@ -585,6 +618,15 @@ extern "C" int lb_cast_weight(const void* src, int src_dtype, void* dst16, void*
     cast_weight_kernel<uint16_t><<<grid, block, 0, st>>>(reinterpret_cast<const uint16_t*>(src), src_dtype == LB_BF16, d, dT, R, C, fmt);
   else
     return LB_ERR_DTYPE;
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
+extern "C" int lb_split_bf16x3(const float* src, long long src_rs, void* dst16, int R, int C,
+                               int pattern, void* stream) {
+  if (R <= 0 || C <= 0 || (pattern != 0 && pattern != 1)) return LB_ERR_SHAPE;
+  dim3 grid((C + 255) / 256, R);
+  split_bf16x3_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, src_rs, reinterpret_cast<uint16_t*>(dst16), R, C, pattern);
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }
 

@@ -27,6 +27,20 @@ from . import ops
 from ._C import LoraB200Error
 
 _LOW = (torch.bfloat16, torch.float16)
+_FP32_MODE = "bf16"   # fp32 activations outside autocast: "bf16" operands, or "split" (precise_path.py)
+
+
+def set_fp32_mode(mode: str):
+    """Policy for fp32 activations outside autocast: "bf16" (default: bf16 operands, fp32
+    accumulate and output) or "split" (3-term split-bf16 operands, fp32-faithful; 3x tensor work)."""
+    global _FP32_MODE
+    if mode not in ("bf16", "split"):
+        raise ValueError("fp32 mode must be 'bf16' or 'split'")
+    _FP32_MODE = mode
+
+
+def get_fp32_mode() -> str:
+    return _FP32_MODE
 
 
 def _compute_dtype(x: torch.Tensor) -> torch.dtype:
@@ -237,6 +251,10 @@ class LoraInjectedLinear(nn.Module):
         if self.training and self.dropout.p > 0.0:
             from .dropout_path import lora_linear_dropout
             return lora_linear_dropout(self, input)
+        if (_FP32_MODE == "split" and input.dtype == torch.float32 and self.linear.weight.dtype == torch.float32
+                and not torch.is_autocast_enabled("cuda")):
+            from .precise_path import lora_linear_precise
+            return lora_linear_precise(self, input)
         return _FusedLoraLinearFn.apply(input, self.lora_down.weight, self.lora_up.weight, self)
 
     def realize_as_lora(self):
