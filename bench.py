@@ -332,6 +332,11 @@ def cpu_reference(res, rank_r, budget_s=30.0, max_steps=None, warmup=1, tiny=Fal
     from oracle.ref_modules import ref_inject
     from oracle.ref_step import RefDreamboothStep
     from lora_b200.host.ddpm import DDPMNoiser
+    # all the host threads torch can use (torchrun exports OMP_NUM_THREADS=1 for its children)
+    ncpu = os.cpu_count() or 1
+    want = int(os.environ.get("LB_CPU_THREADS", "0")) or (ncpu // 2 if ncpu >= 16 else ncpu)
+    if torch.get_num_threads() < want:
+        torch.set_num_threads(want)
     unet, text = build_models("cpu", torch.float32, seed=0, tiny=tiny)
     us = ref_inject(unet, {"CrossAttention", "Attention", "GEGLU"}, r=rank_r)
     ts = ref_inject(text, {"CLIPAttention"}, r=rank_r)

@@ -64,6 +64,7 @@ class LoraTrainStep:
         self.h_input_ids = torch.zeros((latent_shape[0], seq_len), dtype=torch.long).pin_memory()
         self.h_loss = torch.zeros((), dtype=torch.float32).pin_memory()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_update: Optional[torch.cuda.CUDAGraph] = None
         self.graph_error: Optional[str] = None
         self._world = 1
         import torch.distributed as dist
@@ -73,7 +74,8 @@ class LoraTrainStep:
         self.text_encoder.train()
 
     # ------------------------------------------------------------------ the step body
-    def _body(self):
+    def _fwd_bwd(self):
+        """noise -> text encoder -> UNet -> MSE -> backward; dA/dB land in the arena's g buffer."""
         cfg = self.cfg
         lat = self.latents
         bsz = lat.shape[0]
@@ -93,12 +95,23 @@ class LoraTrainStep:
             pred = self.unet(noisy, timesteps, ehs.to(self.model_dtype)).sample
         loss = F.mse_loss(pred.float(), noise.float(), reduction="mean")
         loss.backward()
-        self.arena.allreduce_grads()
-        self.arena.step(cfg.adam_beta1, cfg.adam_beta2, cfg.adam_epsilon, cfg.adam_weight_decay,
-                        cfg.max_grad_norm, world_size=self._world)
         self.loss.copy_(loss.detach())
 
+    def _update(self):
+        cfg = self.cfg
+        self.arena.step(cfg.adam_beta1, cfg.adam_beta2, cfg.adam_epsilon, cfg.adam_weight_decay,
+                        cfg.max_grad_norm, world_size=self._world)
+
+    def _body(self):
+        """One eager step: forward/backward, the one collective, fused clip+AdamW."""
+        self._fwd_bwd()
+        self.arena.allreduce_grads()
+        self._update()
+
     def _capture(self):
+        """Two graphs around the collective: [forward+backward] - NCCL all-reduce - [clip+AdamW].
+        The all-reduce stays an ordinary stream-ordered NCCL call between the two replays (a
+        collective inside a captured graph would tie every rank's capture to its peers')."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -106,26 +119,32 @@ class LoraTrainStep:
                 self._body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            self._body()
-        self.graph = g
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            self._fwd_bwd()
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, pool=g1.pool()):
+            self._update()
+        self.graph, self.graph_update = g1, g2
 
     # ------------------------------------------------------------------ public API
     def prepare(self):
-        """Warm up and (optionally) capture. Counts graph_warmup + 1 optimizer steps."""
+        """Warm up and (optionally) capture. Counts graph_warmup optimizer steps."""
         if self.cfg.use_cuda_graph and self.graph is None and self.graph_error is None:
             try:
                 self._capture()
             except Exception as e:  # capture refused (e.g. a host sync inside the host model)
                 self.graph_error = f"{type(e).__name__}: {e}"
-                self.graph = None
+                self.graph = self.graph_update = None
                 torch.cuda.synchronize()
+                self.arena.zero_grad()
 
     def step_device(self) -> torch.Tensor:
         """One step on inputs already resident in self.latents / self.input_ids."""
         if self.graph is not None:
             self.graph.replay()
+            self.arena.allreduce_grads()
+            self.graph_update.replay()
         else:
             self._body()
         return self.loss
