@@ -127,7 +127,7 @@ def fused_linear_bytes(M, K, N, r, bias, e=2):
     return e * (M * K + N * K + r * K + M * N) + 4 * N * r + (4 * N if bias else 0) + 4 * M * 16
 
 
-def roofline_sweep(trainer, shapes, iters=10):
+def roofline_sweep(trainer, shapes, iters=10, eager_once=False):
     """All fused-kernel launches of one step (fwd: X[M,K]->Y[M,N]; dX: gY[M,N]->dX[M,K]) with
     private buffers per site, captured in one CUDA graph, timed with CUDA events."""
     from lora_b200 import ops
@@ -150,6 +150,9 @@ def roofline_sweep(trainer, shapes, iters=10):
         for (x, w, bb, d16, b, r) in launches:
             ops.fused_linear(x, w, bb, d16, b, r, 1, None, 1.0, r, dt, True)
 
+    if eager_once:     # ncu mode: the LAST len(launches) fused-kernel launches of the process
+        run(); torch.cuda.synchronize(); run(); torch.cuda.synchronize()
+        return total_bytes, float("nan"), len(launches)
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -231,6 +234,11 @@ def run_native(args):
     ops.LAUNCH_COUNT = 0
     trainer._body()                      # one eager step: records tokens per site + launch count
     launches_per_step = ops.LAUNCH_COUNT
+    if args.roofline_only:               # ncu DRAM-traffic mode: one eager sweep of the fused kernel
+        shapes = site_shapes(unet, seen) + site_shapes(text, seen)
+        rb, _, n_l = roofline_sweep(trainer, shapes, eager_once=True)
+        print(json.dumps({"roofline_only": True, "launches": n_l, "algorithmic_bytes": rb}), flush=True)
+        return None
     if args.profile_steps:               # ncu launch-list mode: a few eager steps, nothing else
         for _ in range(args.profile_steps):
             trainer._body()
@@ -287,6 +295,11 @@ def run_native(args):
         hbm_peak, peak_src = load_peaks()
         rb, rms, n_l = roofline_sweep(trainer, shapes)
         achieved = rb / (rms * 1e-3) / 1e9
+        traffic = None   # DRAM bytes of the same 384 launches, from the committed ncu capture
+        tpath = os.path.join(ROOT, "profiles", "fused_linear_dram_traffic.json")
+        if os.path.exists(tpath) and not args.tiny and not args.extended and args.res == 512 and args.rank == 4:
+            with open(tpath) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_sweep")
         value = world * args.steps / (ms_dev * 1e-3)
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -311,7 +324,7 @@ def run_native(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "fused_lora_linear_kernel (fwd + dX launches of one step)",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None,
+                         "frac": achieved / hbm_peak, "traffic": traffic,
                          "launches": n_l, "algorithmic_bytes": rb, "ms_per_sweep": rms,
                          "avg_launch_us": rms * 1e3 / n_l,
                          "share_of_step": rms / (ms_dev / args.steps), "peak_source": peak_src},
@@ -395,6 +408,7 @@ def main():
     ap.add_argument("--extended", action="store_true", help="configs[2]: extended (conv) LoRA sites")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=0, help="run N eager steps and exit (for ncu)")
+    ap.add_argument("--roofline-only", action="store_true", help="one eager sweep of the fused kernel (for ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU-baseline work")
     args = ap.parse_args()

@@ -144,6 +144,12 @@ int lb_cast_conv_weight(const void* src, int src_dtype, void* dst16, void* dstT1
 int lb_cast_rows_pad16(const float* src, long long src_rs, long long src_cs, void* dst16, int r,
                        int C, int out_dtype, void* stream);
 
+/* Fold a LoRA into its frozen weight: out[n,k] = W[n,k] + alpha * sum_j up[n,j]*down[j,k]
+ * (W, out: LB_F32/LB_BF16/LB_F16 [N,K]; conv weights flattened to [Cout, Cin*kh*kw]; out may alias W).
+ * Replaces the up@down GEMM + add of collapse_lora, lora_diffusion/lora.py:635-669. */
+int lb_lora_merge(const void* W, int w_dtype, const float* up, const float* down, float alpha, void* out,
+                  int N, int K, int r, void* stream);
+
 /* fp32-faithful mode ("split-bf16"): dst16 [R, 3C] bf16 = three bf16 terms of src [R,C] fp32 side
  * by side along K; pattern 0 (activations) [hi|lo|hi], pattern 1 (weights, factors) [hi|hi|lo], so
  * an ordinary K-major bf16 GEMM over 3C columns evaluates hi*hi + lo*hi + hi*lo (error 2^-16).

@@ -330,6 +330,28 @@ __global__ void split_bf16x3_kernel(const float* __restrict__ src, long long src
   row[2 * C + c] = pattern == 0 ? h : l;
 }
 
+// ------------------------------------------------------------------------------- merge / collapse
+// out[n,k] = W[n,k] + alpha * sum_j up[n,j] * down[j,k]   (lora.py:646-669; conv: flattened [Cout, Cin*kh*kw])
+// HBM-bound over W: one read + one write of the weight, the rank-r factors stay in L1/L2.
+template <typename WT>
+__global__ void __launch_bounds__(256)
+merge_kernel(const WT* __restrict__ W, int w_fmt, const float* __restrict__ up,
+             const float* __restrict__ down, float alpha, WT* __restrict__ out, int N, int K, int r) {
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  const int n0 = blockIdx.y * 8;
+  if (k >= K) return;
+  float d[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) d[j] = (j < r) ? __ldg(down + static_cast<size_t>(j) * K + k) : 0.f;
+  for (int n = n0; n < min(N, n0 + 8); ++n) {
+    float acc = 0.f;
+    for (int j = 0; j < r; ++j) acc += __ldg(up + static_cast<size_t>(n) * r + j) * d[j];
+    const size_t i = static_cast<size_t>(n) * K + k;
+    if constexpr (sizeof(WT) == 4) out[i] = W[i] + alpha * acc;
+    else out[i] = to16(from16(W[i], w_fmt) + alpha * acc, w_fmt);
+  }
+}
+
 // frozen conv weight [Cout,Cin,T] -> forward operand [Cout, T*Cin] and flipped-transposed
 // input-gradient operand [Cin, T*Cout]; one-time per frozen weight, one thread per element
 template <typename SrcT>
@@ -616,6 +638,21 @@ extern "C" int lb_cast_weight(const void* src, int src_dtype, void* dst16, void*
     cast_weight_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(src), 0, d, dT, R, C, fmt);
   else if (src_dtype == LB_BF16 || src_dtype == LB_F16)
     cast_weight_kernel<uint16_t><<<grid, block, 0, st>>>(reinterpret_cast<const uint16_t*>(src), src_dtype == LB_BF16, d, dT, R, C, fmt);
+  else
+    return LB_ERR_DTYPE;
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
+extern "C" int lb_lora_merge(const void* W, int w_dtype, const float* up, const float* down, float alpha,
+                             void* out, int N, int K, int r, void* stream) {
+  if (N <= 0 || K <= 0) return LB_ERR_SHAPE;
+  if (r < 1 || r > 16) return LB_ERR_RANK;
+  dim3 grid((K + 255) / 256, (N + 7) / 8);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (w_dtype == LB_F32)
+    merge_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(W), 0, up, down, alpha, reinterpret_cast<float*>(out), N, K, r);
+  else if (w_dtype == LB_BF16 || w_dtype == LB_F16)
+    merge_kernel<uint16_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(W), w_dtype == LB_BF16, up, down, alpha, reinterpret_cast<uint16_t*>(out), N, K, r);
   else
     return LB_ERR_DTYPE;
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;

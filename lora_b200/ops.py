@@ -212,3 +212,19 @@ def wgrad_pair(x2d: torch.Tensor, dTs: torch.Tensor, dA: torch.Tensor, gy2d: tor
                                     1, r, N, ptr(diag), float(scale), M, r, float(p), ptr(seed),
                                     dtype_code(x2d.dtype), stream_ptr()), "lb_lora_wgrad_pair")
     _count()
+
+
+def merge_lora(W: torch.Tensor, up: torch.Tensor, down: torch.Tensor, alpha: float) -> torch.Tensor:
+    """W + alpha * up.flatten(1) @ down.flatten(1), same shape/dtype as W (new tensor)."""
+    _req_cuda(W, up, down)
+    w2 = W.detach().contiguous()
+    N = w2.shape[0]
+    K = w2.numel() // N
+    r = down.shape[0]
+    u = up.detach().reshape(N, r).float().contiguous()
+    d = down.detach().reshape(r, K).float().contiguous()
+    out = torch.empty_like(w2)
+    check(_C.lib.lb_lora_merge(ptr(w2), dtype_code(w2.dtype), ptr(u), ptr(d), float(alpha), ptr(out), N, K, r,
+                               stream_ptr()), "lb_lora_merge")
+    _count()
+    return out

@@ -315,3 +315,33 @@ def test_extended_training_step_matches_reference_step_tiny():
         torch.manual_seed(300 + step)
         l_ours = float(tr.step_device())
         assert abs(l_ours - l_ref) < 1e-2 * abs(l_ref), (step, l_ours, l_ref)
+
+
+def test_collapse_lora_on_gpu_matches_oracle():
+    """collapse_lora on CUDA models runs lb_lora_merge (one pass over W): W + alpha*up@down."""
+    import lora_b200 as L
+    from oracle import lora_ops as O
+    torch.manual_seed(0)
+
+    class Attention(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.to_q = nn.Linear(320, 640, bias=False)
+
+    class ResnetBlock2D(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = nn.Conv2d(64, 96, 3, padding=1)
+
+    for dt in (torch.float32, torch.bfloat16):
+        model = nn.Sequential(Attention(), ResnetBlock2D()).to(DEV).to(dt)
+        L.inject_trainable_lora_extended(model, r=8)
+        lin, conv = [m for m in model.modules() if type(m).__name__.startswith("LoraInjected")]
+        lin.lora_up.weight.data.normal_(0, 0.1); conv.lora_up.weight.data.normal_(0, 0.1)
+        w_lin, w_conv = lin.linear.weight.data.clone(), conv.conv.weight.data.clone()
+        L.collapse_lora(model, alpha=0.7)
+        want_lin = w_lin.double().cpu() + O.collapse_delta(lin.lora_down.weight, lin.lora_up.weight, 0.7)
+        want_conv = w_conv.double().cpu() + O.collapse_delta(conv.lora_down.weight, conv.lora_up.weight, 0.7).reshape(w_conv.shape)
+        tol = 1e-6 if dt == torch.float32 else 2 ** -8
+        assert lin.linear.weight.dtype == dt and rel(lin.linear.weight, want_lin) < tol
+        assert conv.conv.weight.shape == w_conv.shape and rel(conv.conv.weight, want_conv) < tol
