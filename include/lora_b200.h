@@ -144,6 +144,17 @@ int lb_cast_conv_weight(const void* src, int src_dtype, void* dst16, void* dstT1
 int lb_cast_rows_pad16(const float* src, long long src_rs, long long src_cs, void* dst16, int r,
                        int C, int out_dtype, void* stream);
 
+/* Pivotal-tuning phase 1 (textual inversion) update of the n trained token rows, one launch:
+ * AdamW on rows [n,D] (fp32 masters; grad is zeroed), t = ++(*step_dev), then, if clip_decay,
+ *   w <- w/||w|| * (||w|| + min(1, 100*lr) * (target_norm - ||w||))        (target_norm = 0.4)
+ * and the row is written into table[token_ids[j], :] (LB_F32/LB_BF16/LB_F16). Equivalent to the
+ * reference's AdamW over the WHOLE embedding table followed by restoring every untouched row,
+ * lora_diffusion/cli_lora_pti.py:448-479. */
+int lb_ti_embed_step(float* rows, float* grad, float* m, float* v, const long long* token_ids, void* table,
+                     int table_dtype, int n_rows, int D, const float* lr_dev, float beta1, float beta2,
+                     float eps, float weight_decay, int* step_dev, int clip_decay, float target_norm,
+                     void* stream);
+
 /* Fold a LoRA into its frozen weight: out[n,k] = W[n,k] + alpha * sum_j up[n,j]*down[j,k]
  * (W, out: LB_F32/LB_BF16/LB_F16 [N,K]; conv weights flattened to [Cout, Cin*kh*kw]; out may alias W).
  * Replaces the up@down GEMM + add of collapse_lora, lora_diffusion/lora.py:635-669. */

@@ -466,6 +466,56 @@ adamw_update_kernel(float* __restrict__ p, float* __restrict__ g, float* __restr
   }
 }
 
+// ------------------------------------------------------------------------------- textual inversion step
+__global__ void bump_step_kernel(int* step_dev) { step_dev[0] += 1; }
+
+// One CTA per trained token row: AdamW on the row (the reference runs AdamW over the whole
+// 49408 x 768 table and then copies every other row back: cli_lora_pti.py:448,477-479 -- the net
+// effect is an update of the placeholder rows only), then the norm "decay" of
+// cli_lora_pti.py:451-468:  w <- w/||w|| * (n + lambda (0.4 - n)),  n = ||w||, lambda = min(1, 100 lr),
+// and the write-back of the row into the embedding table used by the text encoder.
+__global__ void __launch_bounds__(256)
+ti_step_kernel(float* __restrict__ rows, float* __restrict__ grad, float* __restrict__ m,
+               float* __restrict__ v, const long long* __restrict__ token_ids, void* __restrict__ table,
+               int table_dtype, int D, const float* __restrict__ lr_dev, float beta1, float beta2,
+               float eps, float wd, const int* __restrict__ step_dev, int clip_decay, float target_norm) {
+  __shared__ float sh[8];
+  const int j = blockIdx.x;
+  float* w = rows + static_cast<size_t>(j) * D;
+  float* g = grad + static_cast<size_t>(j) * D;
+  float* mm = m + static_cast<size_t>(j) * D;
+  float* vv = v + static_cast<size_t>(j) * D;
+  const float lr = lr_dev[0];
+  const int t = step_dev[0];
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), static_cast<double>(t)));
+  const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(t))));
+  float sq = 0.f;
+  for (int i = threadIdx.x; i < D; i += 256) {
+    const float gi = g[i];
+    float p = w[i] * (1.f - lr * wd);
+    const float m1 = beta1 * mm[i] + (1.f - beta1) * gi;
+    const float v1 = beta2 * vv[i] + (1.f - beta2) * gi * gi;
+    p -= (lr / bc1) * (m1 / (sqrtf(v1) / bc2_sqrt + eps));
+    w[i] = p; mm[i] = m1; vv[i] = v1; g[i] = 0.f;
+    sq += p * p;
+  }
+  const float norm = sqrtf(block_sum(sq, sh));
+  float mult = 1.f;
+  if (clip_decay) {
+    const float lambda = fminf(1.f, 100.f * lr);
+    mult = (norm + lambda * (target_norm - norm)) / fmaxf(norm, 1e-12f);
+  }
+  const long long tok = token_ids[j];
+  for (int i = threadIdx.x; i < D; i += 256) {
+    const float p = w[i] * mult;
+    w[i] = p;
+    const size_t o = static_cast<size_t>(tok) * D + i;
+    if (table_dtype == LB_F32) reinterpret_cast<float*>(table)[o] = p;
+    else reinterpret_cast<uint16_t*>(table)[o] = to16(p, table_dtype == LB_BF16);
+  }
+}
+
+
 }  // namespace lb
 
 // =============================================================================== C ABI
@@ -640,6 +690,20 @@ extern "C" int lb_cast_weight(const void* src, int src_dtype, void* dst16, void*
     cast_weight_kernel<uint16_t><<<grid, block, 0, st>>>(reinterpret_cast<const uint16_t*>(src), src_dtype == LB_BF16, d, dT, R, C, fmt);
   else
     return LB_ERR_DTYPE;
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
+extern "C" int lb_ti_embed_step(float* rows, float* grad, float* m, float* v, const long long* token_ids,
+                                void* table, int table_dtype, int n_rows, int D, const float* lr_dev,
+                                float beta1, float beta2, float eps, float weight_decay, int* step_dev,
+                                int clip_decay, float target_norm, void* stream) {
+  if (n_rows <= 0 || D <= 0) return LB_ERR_SHAPE;
+  if (table_dtype != LB_F32 && table_dtype != LB_BF16 && table_dtype != LB_F16) return LB_ERR_DTYPE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // t = ++(*step_dev) on the stream, before the update reads it
+  bump_step_kernel<<<1, 1, 0, st>>>(step_dev);
+  ti_step_kernel<<<n_rows, 256, 0, st>>>(rows, grad, m, v, token_ids, table, table_dtype, D, lr_dev, beta1,
+                                         beta2, eps, weight_decay, step_dev, clip_decay, target_norm);
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }
 
