@@ -345,3 +345,70 @@ def test_collapse_lora_on_gpu_matches_oracle():
         tol = 1e-6 if dt == torch.float32 else 2 ** -8
         assert lin.linear.weight.dtype == dt and rel(lin.linear.weight, want_lin) < tol
         assert conv.conv.weight.shape == w_conv.shape and rel(conv.conv.weight, want_conv) < tol
+
+
+def test_module_under_gradient_checkpointing():
+    """The reference's trainers enable gradient checkpointing (train_lora_dreambooth.py:627-630):
+    the site is re-run in backward. Gradients must equal the non-checkpointed ones."""
+    from torch.utils.checkpoint import checkpoint
+    ours, _ = _pair(640, 640, 4, True, 1.0, dtype=torch.bfloat16)
+    x = torch.randn(3, 100, 640, device=DEV, dtype=torch.bfloat16)
+    gy = torch.randn(3, 100, 640, device=DEV, dtype=torch.bfloat16)
+    grads = []
+    for use_ckpt in (False, True):
+        xi = x.clone().requires_grad_(True)
+        for p in (ours.lora_down.weight, ours.lora_up.weight):
+            p.grad = None
+        y = checkpoint(ours, xi, use_reentrant=False) if use_ckpt else ours(xi)
+        y.backward(gy)
+        grads.append((xi.grad.clone(), ours.lora_down.weight.grad.clone(), ours.lora_up.weight.grad.clone()))
+    assert torch.equal(grads[0][0], grads[1][0])
+    assert rel(grads[1][1], grads[0][1]) < 1e-5 and rel(grads[1][2], grads[0][2]) < 1e-5   # atomics order
+
+
+def test_fp16_autocast_like_the_pti_trainer():
+    """cli_lora_pti.py:315-316 runs torch.cuda.amp.autocast() = fp16, no GradScaler."""
+    from oracle import lora_ops as O
+    ours, ref = _pair(768, 1280, 16, True, 0.5)
+    x = torch.randn(2, 77, 768, device=DEV, requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = ours(x)
+        y_ref = ref(x.detach())
+    assert y.dtype == torch.float16
+    assert rel(y, y_ref) < 2 ** -9
+    y.float().sum().backward()
+    dX, dA, dB = O.lora_linear_backward(torch.ones(154, 1280), x.detach().reshape(154, 768).half(),
+                                        ours.linear.weight.half(), ours.lora_down.weight, ours.lora_up.weight, 0.5)
+    assert rel(x.grad.reshape(154, 768), dX) < 2e-3
+    assert rel(ours.lora_down.weight.grad, dA) < 2e-3 and rel(ours.lora_up.weight.grad, dB) < 2e-3
+
+
+def test_batched_and_single_row_inputs():
+    """Prior-preservation batches (bs 2) and the ResnetBlock2D time_emb_proj site (one row per image)."""
+    from oracle import lora_ops as O
+    ours, _ = _pair(1280, 320, 8, True, 1.0, dtype=torch.bfloat16)
+    for shape in ((2, 1280), (1, 1280), (2, 3, 5, 1280)):
+        x = torch.randn(*shape, device=DEV, dtype=torch.bfloat16)
+        y = ours(x)
+        assert y.shape == (*shape[:-1], 320)
+        want = O.lora_linear_forward(x.reshape(-1, 1280), ours.linear.weight, ours.linear.bias,
+                                     ours.lora_down.weight, ours.lora_up.weight, 1.0)
+        assert rel(y.reshape(-1, 320), want) < 2 ** -7
+
+
+def test_state_dict_and_device_moves():
+    """Modules are built on CPU and moved (`_tmp.to(device).to(dtype)`, lora.py:295); state_dict keys
+    are the reference's; loading a state_dict in place is picked up (version counter)."""
+    import lora_b200 as L
+    from oracle import lora_ops as O
+    torch.manual_seed(0)
+    m = L.LoraInjectedLinear(320, 320, bias=True, r=4, dropout_p=0.0)
+    sd = {k: torch.randn_like(v) * 0.05 for k, v in m.state_dict().items()}
+    m = m.to(DEV).to(torch.bfloat16)
+    x = torch.randn(64, 320, device=DEV, dtype=torch.bfloat16)
+    _ = m(x)
+    m.load_state_dict(sd)                        # copy_ into existing Parameters: versions bump
+    y = m(x)
+    want = O.lora_linear_forward(x, sd["linear.weight"].to(torch.bfloat16), sd["linear.bias"].to(torch.bfloat16),
+                                 sd["lora_down.weight"].to(torch.bfloat16), sd["lora_up.weight"].to(torch.bfloat16), 1.0)
+    assert rel(y, want) < 2 ** -7
