@@ -230,9 +230,12 @@ def run_native(args):
     host_ids = [torch.randint(0, vocab, (1, seq)).pin_memory() for _ in range(n_data)]
     trainer.latents.copy_(host_lat[0]); trainer.input_ids.copy_(host_ids[0])
 
+    if not args.no_group:
+        L.set_grouping(True)             # q/k/v-type sites that share an input: one launch per family
     seen, hooks = record_tokens(unet, text)
+    trainer._body()                      # eager step 1: records tokens per site, learns site families
     ops.LAUNCH_COUNT = 0
-    trainer._body()                      # one eager step: records tokens per site + launch count
+    trainer._body()                      # eager step 2: the steady-state launch count
     launches_per_step = ops.LAUNCH_COUNT
     if args.roofline_only:               # ncu DRAM-traffic mode: one eager sweep of the fused kernel
         shapes = site_shapes(unet, seen) + site_shapes(text, seen)
@@ -312,7 +315,7 @@ def run_native(args):
                        "extended": bool(args.extended),
                        "resolution": res, "rank": args.rank, "global_batch": world,
                        "lora_sites": len(shapes), "lora_params": trainer.arena.n_params,
-                       "parallelism": f"dp{world}", "cuda_graph": trainer.graph is not None,
+                       "parallelism": f"dp{world}", "cuda_graph": trainer.graph is not None, "grouped_launches": not args.no_group,
                        "graph_error": trainer.graph_error,
                        "l2": "working set per step (>=1.7 GB frozen weights + activations) exceeds the 126 MB L2; no explicit flush",
                        "loss": loss_dev},
@@ -407,6 +410,7 @@ def main():
     ap.add_argument("--tiny", action="store_true", help="toy widths (smoke only, not a bench)")
     ap.add_argument("--extended", action="store_true", help="configs[2]: extended (conv) LoRA sites")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-group", action="store_true", help="one launch per LoRA site (no grouped launches)")
     ap.add_argument("--profile-steps", type=int, default=0, help="run N eager steps and exit (for ncu)")
     ap.add_argument("--roofline-only", action="store_true", help="one eager sweep of the fused kernel (for ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -56,6 +56,17 @@ int lb_lora_linear_fwd(const void* X, const void* W, const float* bias, const vo
                        float scale, void* Y, float* T_out, const float* T_in, int M, int K, int N,
                        int r, int in_dtype, int out_dtype, void* stream);
 
+/* Up to 4 independent lb_lora_linear_fwd problems of the same operand/output dtype in ONE launch
+ * (sites that share an input -- q/k/v of a self-attention, k/v of a cross-attention, CLIP's k/v/q --
+ * each under-fill 148 SMs on their own). All array arguments are HOST arrays of length n; per-problem
+ * semantics are exactly lb_lora_linear_fwd's (T_in unsupported). */
+int lb_lora_linear_fwd_grouped(int n, const void* const* X, const void* const* W,
+                               const float* const* bias, const void* const* down16,
+                               const float* const* up, const long long* up_rs, const long long* up_cs,
+                               const float* const* diag, const float* scale, void* const* Y,
+                               float* const* T_out, const int* M, const int* K, const int* N,
+                               const int* r, int in_dtype, int out_dtype, void* stream);
+
 /* Benchmark/profiling knob: tile schedule of lb_lora_linear_fwd. 0 = auto (default),
  * 1 = one tile per CTA, 2 = persistent CTAs with double-buffered TMEM accumulators. */
 int lb_debug_set_linear_mode(int mode);

@@ -5,5 +5,6 @@ from .lora import (_find_children, _find_modules, _find_modules_v2, _text_lora_p
                    _ti_lora_path)
 
 from .modules import get_fp32_mode, set_fp32_mode  # noqa: F401,E402
+from .grouping import get_grouping, set_grouping  # noqa: F401,E402
 
 __version__ = "0.1.0"

@@ -90,11 +90,11 @@ struct Smem {
   static_assert(ACC_COLS <= 512, "TMEM budget exceeded");
 };
 
-template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G, int MIN_CTAS = 1>
-__global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
-fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY,
-                  const FusedParams p) {
+// One output tile (n_blk, m_blk) of one problem; called by the single-problem and the grouped kernel.
+template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G>
+__device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtensorMap& tmW,
+                                           const CUtensorMap& tmD, const CUtensorMap& tmY,
+                                           const FusedParams& p, const int n_blk, const int m_blk) {
   using S = Smem<BLOCK_N, STAGES, OutT, G>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -103,7 +103,6 @@ fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   if (threadIdx.x == 0) LB_STAMP(0);   // kernel entry
-  const int n_blk = blockIdx.x, m_blk = blockIdx.y;
   const int n0 = n_blk * BLOCK_N;
   // row-tile origin
   int m0 = m_blk * BLOCK_M;   // LINEAR: first row
@@ -376,6 +375,38 @@ fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     tmem_dealloc(tmem, S::TMEM_COLS);
   }
   if (threadIdx.x == 32) LB_STAMP(9);    // kernel exit
+}
+
+template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G, int MIN_CTAS = 1>
+__global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
+fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY,
+                  const FusedParams p) {
+  fused_tile<BLOCK_N, STAGES, OutT, CONV, G>(tmX, tmW, tmD, tmY, p, blockIdx.x, blockIdx.y);
+}
+
+// Several same-dtype linear problems in ONE launch (sites that share an input: q/k/v of an
+// attention block, k/v of every cross-attention, CLIP's k/v/q): a CTA looks up which problem its
+// tile belongs to. Small sites under-fill 148 SMs on their own; together they run in the time of one.
+constexpr int MAX_GROUP = 4;
+struct GroupedArgs {
+  CUtensorMap tmX[MAX_GROUP], tmW[MAX_GROUP], tmD[MAX_GROUP], tmY[MAX_GROUP];
+  FusedParams p[MAX_GROUP];
+  int tile_start[MAX_GROUP + 1];   // prefix sum of tiles per problem
+  int n_tiles_n[MAX_GROUP];        // tiles along N per problem
+  int n_problems;
+};
+
+template <int BLOCK_N, int STAGES, typename OutT, int MIN_CTAS = 1>
+__global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
+fused_lora_grouped_kernel(const __grid_constant__ GroupedArgs a) {
+  int q = 0;
+#pragma unroll
+  for (int i = 1; i < MAX_GROUP; ++i)
+    if (i < a.n_problems && static_cast<int>(blockIdx.x) >= a.tile_start[i]) q = i;
+  const int local = blockIdx.x - a.tile_start[q];
+  const int n_blk = local % a.n_tiles_n[q], m_blk = local / a.n_tiles_n[q];
+  fused_tile<BLOCK_N, STAGES, OutT, false, 1>(a.tmX[q], a.tmW[q], a.tmD[q], a.tmY[q], a.p[q], n_blk, m_blk);
 }
 
 }  // namespace lb

@@ -61,6 +61,36 @@ static int launch_persistent(const void* X, const void* W, const void* Dn, void*
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }
 
+template <int BLOCK_N, int STAGES, typename OutT, int MIN_CTAS>
+static int launch_grouped(GroupedArgs& a, const void* const* X, const void* const* W,
+                          const void* const* Dn, void* const* Y, int out_dtype, cudaStream_t stream) {
+  using S = Smem<BLOCK_N, STAGES, OutT, 1>;
+  auto kern = fused_lora_grouped_kernel<BLOCK_N, STAGES, OutT, MIN_CTAS>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES) != cudaSuccess)
+      return LB_ERR_CUDA;
+    attr_set = true;
+  }
+  const int fmt = a.p[0].fmt;
+  const CUtensorMapDataType in_dt = fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
+  int total = 0;
+  for (int i = 0; i < a.n_problems; ++i) {
+    const FusedParams& p = a.p[i];
+    if (!tmap_2d(&a.tmX[i], X[i], in_dt, 2, p.K, p.M, BLOCK_K, BLOCK_M, true)) return LB_ERR_TMAP;
+    if (!tmap_2d(&a.tmW[i], W[i], in_dt, 2, p.K, p.N, BLOCK_K, BLOCK_N, true)) return LB_ERR_TMAP;
+    if (!tmap_2d(&a.tmD[i], Dn[i], in_dt, 2, p.K, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
+    if (!tmap_2d(&a.tmY[i], Y[i], out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
+    a.tile_start[i] = total;
+    a.n_tiles_n[i] = (p.N + BLOCK_N - 1) / BLOCK_N;
+    total += a.n_tiles_n[i] * ((p.M + BLOCK_M - 1) / BLOCK_M);
+  }
+  for (int i = a.n_problems; i <= MAX_GROUP; ++i) a.tile_start[i] = total;
+  kern<<<total, NUM_THREADS, S::DYN_BYTES, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
 static int g_linear_mode = 0;
 static unsigned long long* g_dbg = nullptr;  // profiling: device buffer of 16 timestamps  // 0 = auto, 1 = one tile per CTA (2-3 CTAs/SM), 2 = persistent
 
@@ -137,4 +167,49 @@ extern "C" int lb_lora_linear_fwd(const void* X, const void* W, const float* bia
                    : launch_linear<64, 7, uint16_t, 1>(X, W, down16, Y, p, out_dtype, st);
   return crowded ? launch_linear<128, 2, uint16_t, 2>(X, W, down16, Y, p, out_dtype, st)
                  : launch_linear<128, 4, uint16_t, 1>(X, W, down16, Y, p, out_dtype, st);
+}
+
+
+extern "C" int lb_lora_linear_fwd_grouped(int n, const void* const* X, const void* const* W,
+                                          const float* const* bias, const void* const* down16,
+                                          const float* const* up, const long long* up_rs,
+                                          const long long* up_cs, const float* const* diag,
+                                          const float* scale, void* const* Y, float* const* T_out,
+                                          const int* M, const int* K, const int* N, const int* r,
+                                          int in_dtype, int out_dtype, void* stream) {
+  using namespace lb;
+  if (n < 1 || n > MAX_GROUP) return LB_ERR_SHAPE;
+  if (in_dtype != LB_BF16 && in_dtype != LB_F16) return LB_ERR_DTYPE;
+  if (out_dtype != in_dtype && out_dtype != LB_F32) return LB_ERR_DTYPE;
+  static GroupedArgs a;   // 2.7 KB of kernel parameters; filled per call (single host thread per process)
+  a.n_problems = n;
+  long long tiles128 = 0, tiles64 = 0;
+  for (int i = 0; i < n; ++i) {
+    if (M[i] <= 0 || N[i] <= 0 || K[i] <= 0 || (K[i] % 8) != 0) return LB_ERR_SHAPE;
+    if (out_dtype == LB_F32 ? (N[i] % 4) != 0 : (N[i] % 8) != 0) return LB_ERR_SHAPE;
+    if (r[i] < 1 || r[i] > R_PAD) return LB_ERR_RANK;
+    if ((reinterpret_cast<uintptr_t>(X[i]) | reinterpret_cast<uintptr_t>(W[i]) |
+         reinterpret_cast<uintptr_t>(down16[i]) | reinterpret_cast<uintptr_t>(Y[i]) |
+         reinterpret_cast<uintptr_t>(T_out ? T_out[i] : nullptr)) & 15)
+      return LB_ERR_ALIGN;
+    FusedParams p = {};
+    p.bias = bias ? bias[i] : nullptr; p.up = up[i]; p.up_rs = up_rs[i]; p.up_cs = up_cs[i]; p.up_gs = 0;
+    p.diag = diag ? diag[i] : nullptr; p.t_out = T_out ? T_out[i] : nullptr; p.t_in = nullptr;
+    p.scale = scale[i]; p.M = M[i]; p.N = N[i]; p.K = K[i]; p.r = r[i];
+    p.fmt = (in_dtype == LB_BF16) ? 1 : 0; p.t_group = 0; p.dbg = nullptr;
+    a.p[i] = p;
+    tiles128 += static_cast<long long>((M[i] + 127) / 128) * ((N[i] + 127) / 128);
+    tiles64 += static_cast<long long>((M[i] + 127) / 128) * ((N[i] + 63) / 64);
+  }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool narrow = tiles128 < 120;
+  const bool crowded = (narrow ? tiles64 : tiles128) > 148;
+  if (out_dtype == LB_F32)
+    return narrow ? launch_grouped<64, 3, float, 2>(a, X, W, down16, Y, out_dtype, st)
+                  : launch_grouped<128, 4, float, 1>(a, X, W, down16, Y, out_dtype, st);
+  if (narrow)
+    return crowded ? launch_grouped<64, 2, uint16_t, 3>(a, X, W, down16, Y, out_dtype, st)
+                   : launch_grouped<64, 7, uint16_t, 1>(a, X, W, down16, Y, out_dtype, st);
+  return crowded ? launch_grouped<128, 2, uint16_t, 2>(a, X, W, down16, Y, out_dtype, st)
+                 : launch_grouped<128, 4, uint16_t, 1>(a, X, W, down16, Y, out_dtype, st);
 }

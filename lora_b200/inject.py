@@ -15,6 +15,8 @@ LoRA operator as direct parent).
 """
 from typing import Iterable, Iterator, List, Optional, Sequence, Set, Tuple, Type
 
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -92,6 +94,7 @@ def _wrap_conv(child: nn.Conv2d, **kw) -> LoraInjectedConv2d:
 def _finish_site(parent, name, new, loras, params, names):
     parent._modules[name] = new
     site = parent._modules[name]
+    site._lb.parent = weakref.ref(parent)
     params.append(site.lora_up.parameters())
     params.append(site.lora_down.parameters())
     if loras is not None:

@@ -78,8 +78,8 @@ class _SiteState:
         self.bias = None   # (key, bias fp32)
         self.down = {}     # dtype -> (key, down16 [16,K])
         self.upT = {}      # dtype -> (key, upT16 [16,N])
-        self.managed = None  # set by LoraArena: object with .shadow(module, which, dtype)
         self.grad_sink = None  # (gA view, gB view) when the arena owns the gradients
+        self.parent = None     # weakref to the module this site was injected into (grouping.py)
 
     def frozen(self, weight2d: torch.Tensor, dtype, need_t: bool):
         k = _key(weight2d)
@@ -255,6 +255,11 @@ class LoraInjectedLinear(nn.Module):
                 and not torch.is_autocast_enabled("cuda")):
             from .precise_path import lora_linear_precise
             return lora_linear_precise(self, input)
+        from . import grouping
+        if grouping._ENABLED and self._lb.parent is not None:
+            out = grouping.forward_maybe_grouped(self, input)
+            if out is not None:
+                return out
         return _FusedLoraLinearFn.apply(input, self.lora_down.weight, self.lora_up.weight, self)
 
     def realize_as_lora(self):

@@ -228,3 +228,40 @@ def merge_lora(W: torch.Tensor, up: torch.Tensor, down: torch.Tensor, alpha: flo
                                stream_ptr()), "lb_lora_merge")
     _count()
     return out
+
+
+def fused_linear_grouped(problems, out_dtype, want_t: bool):
+    """problems: list (<= 4) of (x2d, w16, bias32|None, down16, up32, up_rs, up_cs, diag|None, scale, r).
+    One launch; returns ([Y_i], [T_i or None])."""
+    import ctypes
+    n = len(problems)
+    assert 1 <= n <= 4
+    VP, LL, I, F = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float
+    ys, ts = [], []
+    for (x, w, b, d, up, rs, cs, diag, sc, r) in problems:
+        _req_cuda(x, w, d, up)
+        assert x.is_contiguous() and w.is_contiguous() and d.is_contiguous() and w.shape[1] == x.shape[1]
+        ys.append(torch.empty((x.shape[0], w.shape[0]), device=x.device, dtype=out_dtype))
+        ts.append(torch.empty((x.shape[0], R_PAD), device=x.device, dtype=torch.float32) if want_t else None)
+    dp = lambda t: None if t is None else t.data_ptr()
+    arr = lambda ty, vals: (ty * n)(*vals)
+    X = arr(VP, [p[0].data_ptr() for p in problems])
+    W = arr(VP, [p[1].data_ptr() for p in problems])
+    B = arr(VP, [dp(p[2]) for p in problems])
+    D = arr(VP, [p[3].data_ptr() for p in problems])
+    U = arr(VP, [p[4].data_ptr() for p in problems])
+    RS = arr(LL, [p[5] for p in problems])
+    CS = arr(LL, [p[6] for p in problems])
+    DG = arr(VP, [dp(p[7]) for p in problems])
+    SC = arr(F, [float(p[8]) for p in problems])
+    Y = arr(VP, [y.data_ptr() for y in ys])
+    T = arr(VP, [dp(t) for t in ts])
+    M = arr(I, [p[0].shape[0] for p in problems])
+    K = arr(I, [p[0].shape[1] for p in problems])
+    N = arr(I, [p[1].shape[0] for p in problems])
+    R = arr(I, [p[9] for p in problems])
+    check(_C.lib.lb_lora_linear_fwd_grouped(n, X, W, B, D, U, RS, CS, DG, SC, Y, T, M, K, N, R,
+                                            dtype_code(problems[0][0].dtype), dtype_code(out_dtype),
+                                            stream_ptr()), "lb_lora_linear_fwd_grouped")
+    _count()
+    return ys, ts

@@ -3,6 +3,7 @@
 Contract restated from /root/reference/lora_diffusion/lora.py:635-1042. All functions are tree
 surgery or small weight arithmetic; the numerical hot path lives in modules.py / liblora_b200.so.
 """
+import weakref
 from typing import List, Optional, Union
 
 import torch
@@ -46,6 +47,7 @@ def _install_factors(parent, name, new, loras, like):
     up = loras.pop(0)
     down = loras.pop(0)
     site = parent._modules[name]
+    site._lb.parent = weakref.ref(parent)
     site.lora_up.weight = nn.Parameter(up.type(like.dtype))
     site.lora_down.weight = nn.Parameter(down.type(like.dtype))
     site.to(like.device)
