@@ -94,6 +94,12 @@ int lb_lora_wgrad_pair(const void* X, const float* dTs, float* dA, long long dA_
                        long long dB_cs, int N, const float* diag, float scale, int M, int r,
                        float drop_p, const void* seed_dev, int in_dtype, void* stream);
 
+/* lb_lora_wgrad_pair for up to 4 sites that share X (a grouped family), one launch; HOST arrays. */
+int lb_lora_wgrad_multi(int n, const void* X, const float* const* dTs, float* const* dA,
+                        const void* const* gY, const float* const* T, float* const* dB, const int* N,
+                        const float* const* diag, const float* scale, const int* r, int M, int K,
+                        int in_dtype, void* stream);
+
 /* Conv tap of the same reduction: rows of S are the pixels of NHWC images [M/(H*W), H, W, C]; S is
  * read at pixel (h+dy, w+dx), zero outside the image (the convolution's zero padding):
  *     out[...] += scale * diag[j] * sum_p V[p,j] * S[p shifted by (dy,dx), c]

@@ -64,13 +64,17 @@ struct WgProblem {
   long long js, cs;
   int C;
   float drop_p;        // > 0: S is masked (dropout site), mask index m*C + c
-};
-struct WgArgs {
-  WgProblem pr[2];     // dA and dB of one site share a launch (pr[1].C == 0: single problem)
-  const float* diag;
-  const unsigned long long* seed_dev;
+  const float* diag;   // selector diagonal of this problem's site (or null)
   float scale;
-  int M, r, fmt;
+  int r;
+};
+constexpr int WG_MAXP = 8;
+struct WgArgs {
+  WgProblem pr[WG_MAXP];  // dA and dB of up to 4 sites share a launch
+  int nb_start[WG_MAXP + 1];  // prefix sum of 128-column blocks per problem
+  int n_pr;
+  const unsigned long long* seed_dev;
+  int M, fmt;
   int cH, cW, dy, dx;  // conv tap shift of problem 0 (cH == 0: none)
   int slabs;           // 64-row slabs per CTA
 };
@@ -80,10 +84,12 @@ __global__ void __launch_bounds__(WG_WARPS * 32)
 wgrad_kernel(const WgArgs a) {
   __shared__ float red[RQ * 4][WG_COLS];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nb0 = (a.pr[0].C + WG_COLS - 1) / WG_COLS;
-  const int which = (static_cast<int>(blockIdx.x) >= nb0) ? 1 : 0;
+  int which = 0;
+#pragma unroll
+  for (int i = 1; i < WG_MAXP; ++i)
+    if (i < a.n_pr && static_cast<int>(blockIdx.x) >= a.nb_start[i]) which = i;
   const WgProblem& P = a.pr[which];
-  const int cblk = which ? blockIdx.x - nb0 : blockIdx.x;
+  const int cblk = blockIdx.x - a.nb_start[which];
   const int C = P.C;
   const int c0 = cblk * WG_COLS + lane * 4;
   const bool col_ok = c0 < C;                          // C % 8 == 0 => whole 4-column group valid
@@ -175,8 +181,8 @@ wgrad_kernel(const WgArgs a) {
   for (int idx = threadIdx.x; idx < RQ * 4 * WG_COLS; idx += WG_WARPS * 32) {
     const int j = idx / WG_COLS, c = idx % WG_COLS;
     const int cg = cblk * WG_COLS + c;
-    if (j < a.r && cg < C) {
-      const float coef = a.scale * (a.diag ? a.diag[j] : 1.f);
+    if (j < P.r && cg < C) {
+      const float coef = P.scale * (P.diag ? P.diag[j] : 1.f);
       atomicAdd(P.out + j * P.js + cg * P.cs, coef * red[j][c]);
     }
   }
@@ -559,17 +565,19 @@ extern "C" int lb_lora_wgrad_masked(const void* S, const float* V, const float* 
 }
 
 static int wgrad_run(WgArgs& a, int in_dtype, void* stream) {
-  if (a.M <= 0) return LB_ERR_SHAPE;
-  if (a.r < 1 || a.r > 16) return LB_ERR_RANK;
+  if (a.M <= 0 || a.n_pr < 1 || a.n_pr > WG_MAXP) return LB_ERR_SHAPE;
   if (in_dtype != LB_BF16 && in_dtype != LB_F16 && in_dtype != LB_F32) return LB_ERR_DTYPE;
-  int nblk = 0;
-  for (int i = 0; i < 2; ++i) {
+  int nblk = 0, rmax = 0;
+  for (int i = 0; i < a.n_pr; ++i) {
     const WgProblem& P = a.pr[i];
-    if (P.C == 0 && i == 1) continue;
+    if (P.r < 1 || P.r > 16) return LB_ERR_RANK;
     if (P.C <= 0 || (P.C % 8) != 0) return LB_ERR_SHAPE;
     if ((reinterpret_cast<uintptr_t>(P.S) | reinterpret_cast<uintptr_t>(P.V)) & 15) return LB_ERR_ALIGN;
+    a.nb_start[i] = nblk;
     nblk += (P.C + WG_COLS - 1) / WG_COLS;
+    rmax = P.r > rmax ? P.r : rmax;
   }
+  for (int i = a.n_pr; i <= WG_MAXP; ++i) a.nb_start[i] = nblk;
   a.fmt = in_dtype == LB_BF16 ? 1 : (in_dtype == LB_F32 ? 2 : 0);
   // rows per CTA: keep >= ~2 CTAs per SM, but fold slabs together when the grid would be far
   // larger (fewer global atomics per output element)
@@ -579,7 +587,7 @@ static int wgrad_run(WgArgs& a, int in_dtype, void* stream) {
   a.slabs = slabs;
   dim3 grid(nblk, (slabs_total + slabs - 1) / slabs);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch ((a.r + 3) / 4) {
+  switch ((rmax + 3) / 4) {
     case 1: wgrad_kernel<1><<<grid, WG_WARPS * 32, 0, st>>>(a); break;
     case 2: wgrad_kernel<2><<<grid, WG_WARPS * 32, 0, st>>>(a); break;
     case 3: wgrad_kernel<3><<<grid, WG_WARPS * 32, 0, st>>>(a); break;
@@ -597,9 +605,10 @@ static int wgrad_launch(const void* S, const float* V, const float* diag, float 
   WgArgs a = {};
   a.pr[0].S = reinterpret_cast<const uint2*>(S); a.pr[0].V = V; a.pr[0].out = out;
   a.pr[0].js = out_js; a.pr[0].cs = out_cs; a.pr[0].C = C; a.pr[0].drop_p = drop_p;
-  a.pr[1].C = 0;
-  a.diag = diag; a.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
-  a.scale = scale; a.M = M; a.r = r; a.cH = H; a.cW = W; a.dy = dy; a.dx = dx;
+  a.pr[0].diag = diag; a.pr[0].scale = scale; a.pr[0].r = r;
+  a.n_pr = 1;
+  a.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
+  a.M = M; a.cH = H; a.cW = W; a.dy = dy; a.dx = dx;
   return wgrad_run(a, in_dtype, stream);
 }
 
@@ -614,8 +623,32 @@ extern "C" int lb_lora_wgrad_pair(const void* X, const float* dTs, float* dA, lo
   a.pr[0].js = dA_js; a.pr[0].cs = dA_cs; a.pr[0].C = K; a.pr[0].drop_p = 0.f;
   a.pr[1].S = reinterpret_cast<const uint2*>(gY); a.pr[1].V = T; a.pr[1].out = dB;
   a.pr[1].js = dB_js; a.pr[1].cs = dB_cs; a.pr[1].C = N; a.pr[1].drop_p = drop_p;
-  a.diag = diag; a.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
-  a.scale = scale; a.M = M; a.r = r;
+  for (int i = 0; i < 2; ++i) { a.pr[i].diag = diag; a.pr[i].scale = scale; a.pr[i].r = r; }
+  a.n_pr = 2;
+  a.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
+  a.M = M;
+  return wgrad_run(a, in_dtype, stream);
+}
+
+// dA and dB of up to 4 sites that share X (a grouped family) in one launch. HOST arrays of length n.
+extern "C" int lb_lora_wgrad_multi(int n, const void* X, const float* const* dTs, float* const* dA,
+                                   const void* const* gY, const float* const* T, float* const* dB,
+                                   const int* N, const float* const* diag, const float* scale,
+                                   const int* r, int M, int K, int in_dtype, void* stream) {
+  if (n < 1 || 2 * n > WG_MAXP) return LB_ERR_SHAPE;
+  WgArgs a = {};
+  for (int i = 0; i < n; ++i) {
+    WgProblem& pa = a.pr[2 * i];
+    WgProblem& pb = a.pr[2 * i + 1];
+    pa.S = reinterpret_cast<const uint2*>(X); pa.V = dTs[i]; pa.out = dA[i]; pa.js = K; pa.cs = 1; pa.C = K;
+    pb.S = reinterpret_cast<const uint2*>(gY[i]); pb.V = T[i]; pb.out = dB[i]; pb.js = 1; pb.cs = r[i]; pb.C = N[i];
+    pa.drop_p = pb.drop_p = 0.f;
+    pa.diag = pb.diag = diag ? diag[i] : nullptr;
+    pa.scale = pb.scale = scale[i];
+    pa.r = pb.r = r[i];
+  }
+  a.n_pr = 2 * n;
+  a.M = M;
   return wgrad_run(a, in_dtype, stream);
 }
 

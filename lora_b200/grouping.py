@@ -124,6 +124,7 @@ class _GroupedLoraLinearFn(torch.autograd.Function):
         dx = None
         if probs:
             dXs, dTs = ops.fused_linear_grouped(probs, dx_dtype, True)
+            multi, temps = [], []
             for j, i in enumerate(live):
                 m = members[i]
                 A, B = factors[2 * i], factors[2 * i + 1]
@@ -138,11 +139,15 @@ class _GroupedLoraLinearFn(torch.autograd.Function):
                 if need_b:
                     tB = sink[1] if sink is not None else torch.zeros((N, r), device=x2d.device, dtype=torch.float32)
                 if need_a and need_b:
-                    ops.wgrad_pair(x2d, dTs[j], tA, g2ds[i], Ts[i], tB, diag, scale, r)
+                    multi.append((dTs[j], tA, g2ds[i], Ts[i], tB, diag, scale, r))
                 elif need_a:
                     ops.wgrad(x2d, dTs[j], diag, scale, tA, K, 1, r)
                 elif need_b:
                     ops.wgrad(g2ds[i], Ts[i], diag, scale, tB, 1, r, r)
+                temps.append((i, sink, tA, tB, A, B, need_a, need_b))
+            if multi:
+                ops.wgrad_multi(x2d, multi)      # every dA/dB of the family: one launch
+            for (i, sink, tA, tB, A, B, need_a, need_b) in temps:
                 if sink is None:
                     grads[2 * i] = tA.to(A.dtype).view_as(A) if need_a else None
                     grads[2 * i + 1] = tB.to(B.dtype).view_as(B) if need_b else None

@@ -265,3 +265,25 @@ def fused_linear_grouped(problems, out_dtype, want_t: bool):
                                             stream_ptr()), "lb_lora_linear_fwd_grouped")
     _count()
     return ys, ts
+
+
+def wgrad_multi(x2d: torch.Tensor, items):
+    """items: list (<= 4) of (dTs, dA [r,K] fp32, gy2d [M,N], T, dB [N,r] fp32, diag|None, scale, r):
+    all dA/dB of a family that shares x2d in one launch."""
+    import ctypes
+    n = len(items)
+    VP, I, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    M, K = x2d.shape
+    dp = lambda t: None if t is None else t.data_ptr()
+    arr = lambda ty, vals: (ty * n)(*vals)
+    check(_C.lib.lb_lora_wgrad_multi(n, ptr(x2d), arr(VP, [it[0].data_ptr() for it in items]),
+                                     arr(VP, [it[1].data_ptr() for it in items]),
+                                     arr(VP, [it[2].data_ptr() for it in items]),
+                                     arr(VP, [it[3].data_ptr() for it in items]),
+                                     arr(VP, [it[4].data_ptr() for it in items]),
+                                     arr(I, [it[2].shape[1] for it in items]),
+                                     arr(VP, [dp(it[5]) for it in items]),
+                                     arr(F, [float(it[6]) for it in items]),
+                                     arr(I, [it[7] for it in items]), M, K, dtype_code(x2d.dtype),
+                                     stream_ptr()), "lb_lora_wgrad_multi")
+    _count()

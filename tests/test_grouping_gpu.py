@@ -64,8 +64,8 @@ def test_grouped_block_equals_ungrouped_block():
     got = _run(_block(), x, ctx, gy, 3)          # pass 1 learns the families, passes 2-3 use them
     assert got[0][3] == refs[0][3]               # learning pass: same launches as ungrouped
     # 9 sites: q,k,v (one launch), out, geglu, q2, (k2,v2 one launch), out2 -> 6 forward launches
-    # instead of 9, same in backward: 6 fewer fused launches per steady-state pass
-    assert got[2][3] == refs[2][3] - 6, (got[2][3], refs[2][3])
+    # instead of 9; the same for the dX launches and for the dA/dB reductions: 9 fewer per pass
+    assert got[2][3] == refs[2][3] - 9, (got[2][3], refs[2][3])
     for y, dx, grads, _ in got:
         assert rel(y, ref[0]) < 2e-2 and rel(dx, ref[1]) < 2e-2     # bf16 outputs, different tile shapes
         assert set(grads) == set(ref[2])
