@@ -127,28 +127,73 @@ def fused_linear_bytes(M, K, N, r, bias, e=2):
     return e * (M * K + N * K + r * K + M * N) + 4 * N * r + (4 * N if bias else 0) + 4 * M * 16
 
 
-def roofline_sweep(trainer, shapes, iters=10, eager_once=False):
-    """All fused-kernel launches of one step (fwd: X[M,K]->Y[M,N]; dX: gY[M,N]->dX[M,K]) with
-    private buffers per site, captured in one CUDA graph, timed with CUDA events."""
+def site_families(models, tokens_by_module):
+    """Launch groups of the fused kernel in one step: families of sites that share an input run as ONE
+    grouped launch (lora_b200/grouping.py, learned during the eager steps), every other site alone.
+    Returns a list of lists of (M, K, N, r, has_bias)."""
+    fam_of, fams = {}, []
+    for model in models:
+        for mod in model.modules():
+            st = mod.__dict__.get("_lb_groups")
+            if st is None:
+                continue
+            for fam in {id(f): f for f in st.groups.values() if f is not None}.values():
+                if not any(id(m) in fam_of for m in fam):
+                    for m in fam:
+                        fam_of[id(m)] = len(fams)
+                    fams.append(list(fam))
+    out, done = [], set()
+    shape = lambda m: (tokens_by_module[id(m)], m.linear.in_features, m.linear.out_features, m.r,
+                       m.linear.bias is not None)
+    for model in models:
+        for m in model.modules():
+            if type(m).__name__ != "LoraInjectedLinear":
+                continue
+            f = fam_of.get(id(m))
+            if f is None:
+                out.append([shape(m)])
+            elif f not in done:
+                done.add(f)
+                out.append([shape(x) for x in fams[f]])
+    return out
+
+
+def roofline_sweep(trainer, families, iters=10, eager_once=False):
+    """Every fused-kernel launch of one step (forward: X[M,K]->Y[M,N]; dX: gY[M,N]->dX[M,K]; families
+    as grouped launches) with private buffers per site, captured in one CUDA graph, CUDA-event timed."""
     from lora_b200 import ops
     dev = trainer.device
     dt = trainer.cfg.compute_dtype
     launches = []
     total_bytes = 0
-    for (M, K, N, r, bias) in shapes:
-        for (m, k, n) in ((M, K, N), (M, N, K)):        # forward, then dX on the transposed weight
-            x = torch.randn(m, k, device=dev, dtype=dt)
-            w = torch.randn(n, k, device=dev, dtype=dt) * 0.02
-            a = torch.randn(r, k, device=dev)
-            b = torch.randn(n, r, device=dev) * 0.01
-            d16 = ops.cast_rows_pad16(a, k, 1, r, k, dt)
-            bb = torch.zeros(n, device=dev) if (bias and (m, k, n) == (M, K, N)) else None
-            launches.append((x, w, bb, d16, b, r))
-            total_bytes += fused_linear_bytes(m, k, n, r, bb is not None)
+    for fam in families:
+        for bwd in (False, True):
+            probs = []
+            xs = None
+            for (M, K, N, r, bias) in fam:
+                m, k, n = (M, N, K) if bwd else (M, K, N)
+                if bwd or xs is None:                 # forward: the family shares ONE input
+                    x = torch.randn(m, k, device=dev, dtype=dt)
+                    xs = x if not bwd else None
+                    total_bytes += 2 * m * k
+                else:
+                    x = xs
+                w = torch.randn(n, k, device=dev, dtype=dt) * 0.02
+                a = torch.randn(r, k, device=dev)
+                b = torch.randn(n, r, device=dev) * 0.01
+                d16 = ops.cast_rows_pad16(a, k, 1, r, k, dt)
+                bb = torch.zeros(n, device=dev) if (bias and not bwd) else None
+                probs.append((x, w, bb, d16, b, r, 1, None, 1.0, r))
+                total_bytes += fused_linear_bytes(m, k, n, r, bb is not None) - 2 * m * k
+            launches.append(probs)
 
     def run():
-        for (x, w, bb, d16, b, r) in launches:
-            ops.fused_linear(x, w, bb, d16, b, r, 1, None, 1.0, r, dt, True)
+        for probs in launches:
+            if len(probs) == 1:
+                (x, w, bb, d16, b, rs, cs, dg, sc, r) = probs[0]
+                ops.fused_linear(x, w, bb, d16, b, rs, cs, dg, sc, r, dt, True)
+            else:
+                ops.fused_linear_grouped(probs, dt, True)
 
     if eager_once:     # ncu mode: the LAST len(launches) fused-kernel launches of the process
         run(); torch.cuda.synchronize(); run(); torch.cuda.synchronize()
@@ -238,8 +283,8 @@ def run_native(args):
     trainer._body()                      # eager step 2: the steady-state launch count
     launches_per_step = ops.LAUNCH_COUNT
     if args.roofline_only:               # ncu DRAM-traffic mode: one eager sweep of the fused kernel
-        shapes = site_shapes(unet, seen) + site_shapes(text, seen)
-        rb, _, n_l = roofline_sweep(trainer, shapes, eager_once=True)
+        fams = site_families((unet, text), seen)
+        rb, _, n_l = roofline_sweep(trainer, fams, eager_once=True)
         print(json.dumps({"roofline_only": True, "launches": n_l, "algorithmic_bytes": rb}), flush=True)
         return None
     if args.profile_steps:               # ncu launch-list mode: a few eager steps, nothing else
@@ -295,8 +340,9 @@ def run_native(args):
     out = None
     if rank == 0:
         shapes = site_shapes(unet, seen) + site_shapes(text, seen)
+        fams = site_families((unet, text), seen)
         hbm_peak, peak_src = load_peaks()
-        rb, rms, n_l = roofline_sweep(trainer, shapes)
+        rb, rms, n_l = roofline_sweep(trainer, fams)
         achieved = rb / (rms * 1e-3) / 1e9
         traffic = None   # DRAM bytes of the same 384 launches, from the committed ncu capture
         tpath = os.path.join(ROOT, "profiles", "fused_linear_dram_traffic.json")
@@ -325,7 +371,8 @@ def run_native(args):
             "gpu_launches": int(launches_per_step * args.steps * 2),
             "gpu_launches_per_step": int(launches_per_step),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "fused_lora_linear_kernel (fwd + dX launches of one step)",
+            "roofline": {"bound": "hbm", "kernel": "fused_lora_kernel / fused_lora_grouped_kernel / fused_lora_persistent_kernel: every forward + dX launch of the fused LoRA-linear path in one step (families grouped as in the step)",
+                         "sites": 2 * len(shapes),
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic,
                          "launches": n_l, "algorithmic_bytes": rb, "ms_per_sweep": rms,
