@@ -109,4 +109,5 @@ def test_overwrite_base_matches_oracle_on_tiny_models():
         assert rel(ours, Ue @ Ve) < 3e-2
         # and the reference's own output is the same thing up to that threshold choice
         assert abs(hi_eff - hi) < 0.35 * hi
-        assert float(a.lora_up.weight.data.abs().max()) <= hi_ours * 1.02 + 1e-6
+        # nothing sticks out above the clamp level recomputed on the stored (fp16) factors
+        assert float(a.lora_up.weight.data.abs().max()) <= hi_ours * 1.10 + 1e-6
