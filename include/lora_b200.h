@@ -129,6 +129,12 @@ int lb_lora_wgrad_masked(const void* S, const float* V, const float* diag, float
                          long long out_js, long long out_cs, int M, int C, int r, float drop_p,
                          const void* seed_dev, int in_dtype, void* stream);
 
+/* dA[r,Cin,kh,kw] of a LoraInjectedConv2d in ONE launch (all taps; equals kh*kw calls of
+ * lb_lora_wgrad_shift): S = X NHWC rows [M = n_img*H*W, C = Cin], V = gY.B per pixel [M,16]. */
+int lb_lora_wgrad_conv(const void* S, const float* V, const float* diag, float scale, float* out, int M,
+                       int C, int r, int H, int W, int kh, int kw, int pad_h, int pad_w, int in_dtype,
+                       void* stream);
+
 /* Fused frozen Conv2d + LoRA (NHWC implicit GEMM on tcgen05; stride 1, dilation 1, groups 1,
  * 1x1 or 3x3 "same" padding -- the ResnetBlock2D sites of SD1.5):
  *     Y[n,h,w,:] = sum_tap X[n,h+ty-pad,w+tx-pad,:] . W[:, tap, :]^T (+ bias)

@@ -40,6 +40,7 @@ def _load():
                                 f32, f32, f32, vp, vp, vp, vp], i32),
         "lb_refresh_shadows": ([vp, vp, i32, i32, vp, i32, vp], i32),
         "lb_debug_set_linear_mode": ([i32], i32),
+        "lb_lora_wgrad_conv": ([vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
         "lb_lora_wgrad_multi": ([i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp], i32),
         "lb_lora_linear_fwd_grouped": ([i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp,
                                         i32, i32, vp], i32),
@@ -79,7 +80,7 @@ EXPORTED = [n for n in ("lb_abi_version", "lb_lora_linear_fwd", "lb_lora_wgrad",
                         "lb_refresh_shadows", "lb_lora_wgrad_shift", "lb_lora_conv2d_fwd",
                         "lb_cast_conv_weight", "lb_lora_up_dropout", "lb_lora_dropout_dt",
                         "lb_lora_wgrad_masked", "lb_lora_wgrad_pair", "lb_svd_mul", "lb_svd_gram",
-                        "lb_svd_chol_inv", "lb_svd_apply", "lb_svd_jacobi", "lb_svd_randn", "lb_split_bf16x3", "lb_lora_merge", "lb_ti_embed_step", "lb_lora_linear_fwd_grouped", "lb_lora_wgrad_multi")]
+                        "lb_svd_chol_inv", "lb_svd_apply", "lb_svd_jacobi", "lb_svd_randn", "lb_split_bf16x3", "lb_lora_merge", "lb_ti_embed_step", "lb_lora_linear_fwd_grouped", "lb_lora_wgrad_multi", "lb_lora_wgrad_conv")]
 
 
 def check(status: int, what: str):

@@ -76,6 +76,7 @@ struct WgArgs {
   const unsigned long long* seed_dev;
   int M, fmt;
   int cH, cW, dy, dx;  // conv tap shift of problem 0 (cH == 0: none)
+  int kw, taps;        // taps > 1: blockIdx.z = filter tap t: shift (dy + t/kw, dx + t%kw), out += t
   int slabs;           // 64-row slabs per CTA
 };
 
@@ -96,6 +97,8 @@ wgrad_kernel(const WgArgs a) {
   const bool f32in = a.fmt == 2;                       // fp32 rows: 16 bytes per lane
   const size_t pitch = static_cast<size_t>(C) >> 2;    // row pitch in 8-byte words (16-bit rows)
   const int cH = which ? 0 : a.cH;
+  const int tap = (cH > 0 && a.taps > 1) ? blockIdx.z : 0;
+  const int sdy = a.dy + (a.taps > 1 ? tap / a.kw : 0), sdx = a.dx + (a.taps > 1 ? tap % a.kw : 0);
   for (int i = threadIdx.x; i < RQ * 4 * WG_COLS; i += WG_WARPS * 32) (&red[0][0])[i] = 0.f;
   __syncthreads();
 
@@ -115,9 +118,9 @@ wgrad_kernel(const WgArgs a) {
       if (cH > 0 && ok) {
         // conv weight-gradient tap: row m is pixel (h, w) of an NHWC image; S is read at the pixel
         // shifted by (dy, dx), zero outside the image (= the convolution's zero padding)
-        const int ww = m % a.cW + a.dx, hh = (m / a.cW) % cH + a.dy;
+        const int ww = m % a.cW + sdx, hh = (m / a.cW) % cH + sdy;
         ok = hh >= 0 && hh < cH && ww >= 0 && ww < a.cW;
-        src = static_cast<long long>(m) + a.dy * a.cW + a.dx;
+        src = static_cast<long long>(m) + sdy * a.cW + sdx;
       }
       if (!ok) {
         raw[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -183,7 +186,7 @@ wgrad_kernel(const WgArgs a) {
     const int cg = cblk * WG_COLS + c;
     if (j < P.r && cg < C) {
       const float coef = P.scale * (P.diag ? P.diag[j] : 1.f);
-      atomicAdd(P.out + j * P.js + cg * P.cs, coef * red[j][c]);
+      atomicAdd(P.out + j * P.js + cg * P.cs + tap, coef * red[j][c]);
     }
   }
 }
@@ -585,7 +588,7 @@ static int wgrad_run(WgArgs& a, int in_dtype, void* stream) {
   int slabs = 1;
   while (slabs < 8 && static_cast<long long>(nblk) * ((slabs_total + 2 * slabs - 1) / (2 * slabs)) >= 296) slabs *= 2;
   a.slabs = slabs;
-  dim3 grid(nblk, (slabs_total + slabs - 1) / slabs);
+  dim3 grid(nblk, (slabs_total + slabs - 1) / slabs, a.taps > 1 ? a.taps : 1);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch ((rmax + 3) / 4) {
     case 1: wgrad_kernel<1><<<grid, WG_WARPS * 32, 0, st>>>(a); break;
@@ -609,6 +612,22 @@ static int wgrad_launch(const void* S, const float* V, const float* diag, float 
   a.n_pr = 1;
   a.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
   a.M = M; a.cH = H; a.cW = W; a.dy = dy; a.dx = dx;
+  return wgrad_run(a, in_dtype, stream);
+}
+
+// All kh*kw taps of a conv down-factor gradient in one launch: tap t reads S shifted by
+// (t/kw - pad_h, t%kw - pad_w) and accumulates into out[j*out_js + c*out_cs + t].
+extern "C" int lb_lora_wgrad_conv(const void* S, const float* V, const float* diag, float scale,
+                                  float* out, int M, int C, int r, int H, int W, int kh, int kw,
+                                  int pad_h, int pad_w, int in_dtype, void* stream) {
+  if (H <= 0 || W <= 0 || kh <= 0 || kw <= 0 || (M % (H * W)) != 0) return LB_ERR_SHAPE;
+  WgArgs a = {};
+  const int taps = kh * kw;
+  a.pr[0].S = reinterpret_cast<const uint2*>(S); a.pr[0].V = V; a.pr[0].out = out;
+  a.pr[0].js = static_cast<long long>(C) * taps; a.pr[0].cs = taps; a.pr[0].C = C; a.pr[0].drop_p = 0.f;
+  a.pr[0].diag = diag; a.pr[0].scale = scale; a.pr[0].r = r;
+  a.n_pr = 1;
+  a.M = M; a.cH = H; a.cW = W; a.dy = -pad_h; a.dx = -pad_w; a.kw = kw; a.taps = taps;
   return wgrad_run(a, in_dtype, stream);
 }
 

@@ -287,3 +287,14 @@ def wgrad_multi(x2d: torch.Tensor, items):
                                      arr(I, [it[7] for it in items]), M, K, dtype_code(x2d.dtype),
                                      stream_ptr()), "lb_lora_wgrad_multi")
     _count()
+
+
+def wgrad_conv(x_nhwc_rows: torch.Tensor, V: torch.Tensor, diag, scale: float, out: torch.Tensor, r: int,
+               C: int, H: int, W: int, kh: int, kw: int, pad_h: int, pad_w: int):
+    """dA [r, C*kh*kw] (flat [r,Cin,kh,kw]) += all taps, one launch (see lb_lora_wgrad_conv)."""
+    _req_cuda(x_nhwc_rows, V, out)
+    M = V.shape[0]
+    check(_C.lib.lb_lora_wgrad_conv(ptr(x_nhwc_rows), ptr(V), ptr(diag), float(scale), ptr(out), M, C, r,
+                                    H, W, kh, kw, pad_h, pad_w, dtype_code(x_nhwc_rows.dtype), stream_ptr()),
+          "lb_lora_wgrad_conv")
+    _count()

@@ -33,7 +33,7 @@ def _ptr_array(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
 
 
 def _orth2(Y: torch.Tensor, G: torch.Tensor, V: torch.Tensor, sig: torch.Tensor, rows: int, batch: int,
-           sweeps: int = 8):
+           sweeps: int = 6):
     """Orthonormalise the 32 columns of Y in place, twice (like CholeskyQR2, but rank-revealing):
     G = Y^T Y = V diag(s^2) V^T (Jacobi)  ->  Y <- Y V diag(1/s), numerically null directions
     (s < 1e-6 s_max) become zero columns. A Cholesky factor would break down exactly there, and
