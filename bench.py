@@ -245,6 +245,7 @@ def run_native(args):
         raise SystemExit("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    torch.backends.cudnn.benchmark = True   # host-model convs: let cuDNN pick its kernels in warm-up
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
