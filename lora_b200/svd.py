@@ -125,9 +125,13 @@ def overwrite_base(base_model: nn.Module, tuned_model: nn.Module, rank: int, cla
     for (shape, _), items in groups.items():
         ups, downs, _ = svd_lowrank_batched([x[2] for x in items], [x[1] for x in items], rank,
                                             power_iters=power_iters)
+        # cli_svd.py:42-47 for the whole group at once: hi_b = quantile(cat(U_b, Vh_b), q); clamp to [-hi_b, hi_b]
+        b = ups.shape[0]
+        hi = torch.quantile(torch.cat([ups.reshape(b, -1), downs.reshape(b, -1)], dim=1), clamp_quantile, dim=1)
+        ups = torch.minimum(torch.maximum(ups, -hi.view(b, 1, 1)), hi.view(b, 1, 1))
+        downs = torch.minimum(torch.maximum(downs, -hi.view(b, 1, 1)), hi.view(b, 1, 1))
         for i, (site, _, _) in enumerate(items):
             u, d = ups[i], downs[i]
-            _clamp_pair_(u, d, clamp_quantile)
             dev, dt = site.lora_up.weight.device, site.lora_up.weight.dtype
             assert site.lora_up.weight.flatten(1).shape == u.shape
             assert site.lora_down.weight.flatten(1).shape == d.shape
