@@ -39,6 +39,14 @@ class StepConfig:
     # accelerate-style mixed precision (fp32 frozen weights + torch.autocast), the reference's
     # own configuration (train_lora_dreambooth.py:489-494). None: run in the models' own dtype.
     autocast_dtype: Optional[torch.dtype] = None
+    # lr_scheduler: "constant" (train_lora_dreambooth.py default) or "linear" decay to 0 over
+    # max_train_steps after lr_warmup_steps (cli_lora_pti.py:730-741 `lr_scheduler_lora="linear"`)
+    lr_scheduler: str = "constant"
+    lr_warmup_steps: int = 0
+    max_train_steps: int = 1000
+    # PTI masked loss (cli_lora_pti.py:346-368): loss = (mse * mask).mean([1,2,3]).mean(); the mask
+    # is a per-sample latent-resolution weight map held in `self.mask` (ones = plain MSE)
+    use_mask: bool = False
 
 
 class LoraTrainStep:
@@ -59,6 +67,8 @@ class LoraTrainStep:
         self.latents = torch.zeros(latent_shape, device=self.device, dtype=torch.float32)
         self.input_ids = torch.zeros((latent_shape[0], seq_len), device=self.device, dtype=torch.long)
         self.loss = torch.zeros((), device=self.device, dtype=torch.float32)
+        self.mask = torch.ones((latent_shape[0], 1, latent_shape[2], latent_shape[3]), device=self.device)
+        self.global_step = 0
         # pinned host mirrors for the end-to-end path
         self.h_latents = torch.zeros(latent_shape, dtype=torch.float32).pin_memory()
         self.h_input_ids = torch.zeros((latent_shape[0], seq_len), dtype=torch.long).pin_memory()
@@ -93,7 +103,11 @@ class LoraTrainStep:
                     ehs = self.text_encoder(self.input_ids)[0]
             noisy = noisy.to(self.model_dtype).contiguous(memory_format=torch.channels_last)
             pred = self.unet(noisy, timesteps, ehs.to(self.model_dtype)).sample
-        loss = F.mse_loss(pred.float(), noise.float(), reduction="mean")
+        if cfg.use_mask:
+            m = self.mask / self.mask.mean(dim=[1, 2, 3], keepdim=True).clamp_min(1e-6)
+            loss = (F.mse_loss(pred.float() * m, noise.float() * m, reduction="none").mean([1, 2, 3])).mean()
+        else:
+            loss = F.mse_loss(pred.float(), noise.float(), reduction="mean")
         loss.backward()
         self.loss.copy_(loss.detach())
 
@@ -139,8 +153,22 @@ class LoraTrainStep:
                 torch.cuda.synchronize()
                 self.arena.zero_grad()
 
+    def lr_multiplier(self, step: int) -> float:
+        """diffusers `get_scheduler` semantics for the two schedules the reference uses."""
+        cfg = self.cfg
+        if cfg.lr_warmup_steps > 0 and step < cfg.lr_warmup_steps:
+            return float(step) / float(max(1, cfg.lr_warmup_steps))
+        if cfg.lr_scheduler == "linear":
+            return max(0.0, float(cfg.max_train_steps - step) /
+                       float(max(1, cfg.max_train_steps - cfg.lr_warmup_steps)))
+        return 1.0
+
     def step_device(self) -> torch.Tensor:
         """One step on inputs already resident in self.latents / self.input_ids."""
+        if self.cfg.lr_scheduler != "constant" or self.cfg.lr_warmup_steps > 0:
+            mult = self.lr_multiplier(self.global_step)      # host-side schedule, tiny async H2D copy
+            self.arena.set_lr([b * mult for b in self.arena.base_lr])
+        self.global_step += 1
         if self.graph is not None:
             self.graph.replay()
             self.arena.allreduce_grads()

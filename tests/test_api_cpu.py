@@ -253,3 +253,17 @@ def test_fixture_manifest_layout():
                 w, ranks, targets = ours[name]
                 assert len(w) == info["n_weights"] and ranks == info["ranks"] and sorted(targets) == info["targets"]
             assert sorted(L.parse_safeloras_embeds(f)) == ent["embeds"]
+
+
+def test_lr_schedule_restates_diffusers_linear_and_constant():
+    """cli_lora_pti.py:730-741 uses get_scheduler('linear'/'constant'); the multipliers are restated."""
+    from lora_b200.train import LoraTrainStep, StepConfig
+
+    class Dummy:
+        lr_multiplier = LoraTrainStep.lr_multiplier
+    d = Dummy()
+    d.cfg = StepConfig(lr_scheduler="linear", lr_warmup_steps=10, max_train_steps=110)
+    assert d.lr_multiplier(0) == 0.0 and d.lr_multiplier(5) == 0.5 and d.lr_multiplier(10) == 1.0
+    assert abs(d.lr_multiplier(60) - 0.5) < 1e-12 and d.lr_multiplier(110) == 0.0 and d.lr_multiplier(500) == 0.0
+    d.cfg = StepConfig(lr_scheduler="constant")
+    assert d.lr_multiplier(0) == 1.0 and d.lr_multiplier(10 ** 6) == 1.0
