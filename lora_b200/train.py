@@ -44,9 +44,10 @@ class StepConfig:
     lr_scheduler: str = "constant"
     lr_warmup_steps: int = 0
     max_train_steps: int = 1000
-    # PTI masked loss (cli_lora_pti.py:346-368): loss = (mse * mask).mean([1,2,3]).mean(); the mask
-    # is a per-sample latent-resolution weight map held in `self.mask` (ones = plain MSE)
+    # PTI masked loss (cli_lora_pti.py:340-368): mask (latent resolution, in `self.mask`) ->
+    # (mask + 0.01)^mask_temperature / max -> pred*mask, target*mask -> mse.mean([1,2,3]).mean()
     use_mask: bool = False
+    mask_temperature: float = 1.0
 
 
 class LoraTrainStep:
@@ -104,8 +105,9 @@ class LoraTrainStep:
             noisy = noisy.to(self.model_dtype).contiguous(memory_format=torch.channels_last)
             pred = self.unet(noisy, timesteps, ehs.to(self.model_dtype)).sample
         if cfg.use_mask:
-            m = self.mask / self.mask.mean(dim=[1, 2, 3], keepdim=True).clamp_min(1e-6)
-            loss = (F.mse_loss(pred.float() * m, noise.float() * m, reduction="none").mean([1, 2, 3])).mean()
+            m = (self.mask.float() + 0.01).pow(cfg.mask_temperature)
+            m = m / m.max()
+            loss = F.mse_loss((pred * m).float(), (noise * m).float(), reduction="none").mean([1, 2, 3]).mean()
         else:
             loss = F.mse_loss(pred.float(), noise.float(), reduction="mean")
         loss.backward()
