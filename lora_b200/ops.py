@@ -19,6 +19,31 @@ def _count(n: int = 1):
     LAUNCH_COUNT += n
 
 
+# Optional side stream for the factor-gradient reductions: dA/dB are consumed only by the optimizer
+# at the very end of the step, so (when they accumulate straight into the arena) they can run
+# concurrently with the rest of the backward pass, which under-fills the GPU at bs = 1. The trainer
+# sets the stream, and joins it before the all-reduce / optimizer.
+_SIDE = None
+
+
+def set_side_stream(stream):
+    global _SIDE
+    _SIDE = stream
+
+
+def _maybe_side(async_ok: bool, tensors, fn):
+    if _SIDE is None or not async_ok:
+        fn()
+        return
+    cur = torch.cuda.current_stream()
+    _SIDE.wait_stream(cur)                 # everything enqueued so far (incl. the dX kernel) comes first
+    with torch.cuda.stream(_SIDE):
+        fn()
+    for t in tensors:                      # keep the inputs' memory away from the allocator until done
+        if t is not None:
+            t.record_stream(_SIDE)
+
+
 def _req_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -75,14 +100,15 @@ def fused_linear(x2d: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tens
 
 
 def wgrad(S: torch.Tensor, V: torch.Tensor, diag: Optional[torch.Tensor], scale: float,
-          out: torch.Tensor, out_js: int, out_cs: int, r: int):
+          out: torch.Tensor, out_js: int, out_cs: int, r: int, async_ok: bool = False):
     """out[j*out_js + c*out_cs] += scale*diag[j] * sum_m V[m,j]*S[m,c]."""
     _req_cuda(S, V, out)
     M, C = S.shape
     assert S.is_contiguous() and V.shape == (M, R_PAD) and V.dtype == torch.float32
     assert out.dtype == torch.float32
-    check(_C.lib.lb_lora_wgrad(ptr(S), ptr(V), ptr(diag), float(scale), ptr(out), out_js, out_cs,
-                               M, C, r, dtype_code(S.dtype), stream_ptr()), "lb_lora_wgrad")
+    _maybe_side(async_ok, (S, V, diag), lambda: check(
+        _C.lib.lb_lora_wgrad(ptr(S), ptr(V), ptr(diag), float(scale), ptr(out), out_js, out_cs,
+                             M, C, r, dtype_code(S.dtype), stream_ptr()), "lb_lora_wgrad"))
     _count()
 
 
@@ -202,15 +228,16 @@ def wgrad_masked(S: torch.Tensor, V: torch.Tensor, diag, scale: float, out: torc
 
 def wgrad_pair(x2d: torch.Tensor, dTs: torch.Tensor, dA: torch.Tensor, gy2d: torch.Tensor,
                T: torch.Tensor, dB: torch.Tensor, diag, scale: float, r: int, p: float = 0.0,
-               seed: Optional[torch.Tensor] = None):
+               seed: Optional[torch.Tensor] = None, async_ok: bool = False):
     """dA [r,K] += s*d * dTs^T x2d  and  dB [N,r] += s*d * (mask o gy2d)^T T  in one launch."""
     _req_cuda(x2d, dTs, dA, gy2d, T, dB)
     M, K = x2d.shape
     N = gy2d.shape[1]
     assert gy2d.shape[0] == M and dA.dtype == torch.float32 and dB.dtype == torch.float32
-    check(_C.lib.lb_lora_wgrad_pair(ptr(x2d), ptr(dTs), ptr(dA), K, 1, K, ptr(gy2d), ptr(T), ptr(dB),
-                                    1, r, N, ptr(diag), float(scale), M, r, float(p), ptr(seed),
-                                    dtype_code(x2d.dtype), stream_ptr()), "lb_lora_wgrad_pair")
+    _maybe_side(async_ok, (x2d, dTs, gy2d, T, diag, seed), lambda: check(
+        _C.lib.lb_lora_wgrad_pair(ptr(x2d), ptr(dTs), ptr(dA), K, 1, K, ptr(gy2d), ptr(T), ptr(dB),
+                                  1, r, N, ptr(diag), float(scale), M, r, float(p), ptr(seed),
+                                  dtype_code(x2d.dtype), stream_ptr()), "lb_lora_wgrad_pair"))
     _count()
 
 
@@ -267,7 +294,7 @@ def fused_linear_grouped(problems, out_dtype, want_t: bool):
     return ys, ts
 
 
-def wgrad_multi(x2d: torch.Tensor, items):
+def wgrad_multi(x2d: torch.Tensor, items, async_ok: bool = False):
     """items: list (<= 4) of (dTs, dA [r,K] fp32, gy2d [M,N], T, dB [N,r] fp32, diag|None, scale, r):
     all dA/dB of a family that shares x2d in one launch."""
     import ctypes
@@ -276,16 +303,15 @@ def wgrad_multi(x2d: torch.Tensor, items):
     M, K = x2d.shape
     dp = lambda t: None if t is None else t.data_ptr()
     arr = lambda ty, vals: (ty * n)(*vals)
-    check(_C.lib.lb_lora_wgrad_multi(n, ptr(x2d), arr(VP, [it[0].data_ptr() for it in items]),
-                                     arr(VP, [it[1].data_ptr() for it in items]),
-                                     arr(VP, [it[2].data_ptr() for it in items]),
-                                     arr(VP, [it[3].data_ptr() for it in items]),
-                                     arr(VP, [it[4].data_ptr() for it in items]),
-                                     arr(I, [it[2].shape[1] for it in items]),
-                                     arr(VP, [dp(it[5]) for it in items]),
-                                     arr(F, [float(it[6]) for it in items]),
-                                     arr(I, [it[7] for it in items]), M, K, dtype_code(x2d.dtype),
-                                     stream_ptr()), "lb_lora_wgrad_multi")
+    a = (arr(VP, [it[0].data_ptr() for it in items]), arr(VP, [it[1].data_ptr() for it in items]),
+         arr(VP, [it[2].data_ptr() for it in items]), arr(VP, [it[3].data_ptr() for it in items]),
+         arr(VP, [it[4].data_ptr() for it in items]), arr(I, [it[2].shape[1] for it in items]),
+         arr(VP, [dp(it[5]) for it in items]), arr(F, [float(it[6]) for it in items]),
+         arr(I, [it[7] for it in items]))
+    used = [x2d] + [t for it in items for t in (it[0], it[2], it[3], it[5])]
+    _maybe_side(async_ok, used, lambda: check(
+        _C.lib.lb_lora_wgrad_multi(n, ptr(x2d), a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], M, K,
+                                   dtype_code(x2d.dtype), stream_ptr()), "lb_lora_wgrad_multi"))
     _count()
 
 

@@ -36,6 +36,9 @@ class StepConfig:
     compute_dtype: torch.dtype = torch.bfloat16
     use_cuda_graph: bool = True
     graph_warmup: int = 3
+    # run the dA/dB reductions on a side stream, concurrently with the rest of the backward pass
+    # (they feed only the optimizer); joined before the all-reduce
+    async_wgrad: bool = True
     # accelerate-style mixed precision (fp32 frozen weights + torch.autocast), the reference's
     # own configuration (train_lora_dreambooth.py:489-494). None: run in the models' own dtype.
     autocast_dtype: Optional[torch.dtype] = None
@@ -83,6 +86,7 @@ class LoraTrainStep:
             self._world = dist.get_world_size()
         self.unet.train()
         self.text_encoder.train()
+        self._side = torch.cuda.Stream(device=self.device) if cfg.async_wgrad else None
 
     # ------------------------------------------------------------------ the step body
     def _fwd_bwd(self):
@@ -110,7 +114,14 @@ class LoraTrainStep:
             loss = F.mse_loss((pred * m).float(), (noise * m).float(), reduction="none").mean([1, 2, 3]).mean()
         else:
             loss = F.mse_loss(pred.float(), noise.float(), reduction="mean")
-        loss.backward()
+        from . import ops
+        ops.set_side_stream(self._side)
+        try:
+            loss.backward()
+        finally:
+            ops.set_side_stream(None)
+        if self._side is not None:
+            torch.cuda.current_stream().wait_stream(self._side)   # join: all dA/dB are in arena.g
         self.loss.copy_(loss.detach())
 
     def _update(self):
