@@ -248,7 +248,21 @@ def run_native(args):
     torch.backends.cudnn.benchmark = True   # host-model convs: let cuDNN pick its kernels in warm-up
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        os.environ["NCCL_DEBUG"] = os.environ.get("LB_NCCL_DEBUG", "WARN")
+        # NCCL prints its version banner to STDOUT at communicator creation; stdout carries exactly
+        # one JSON line, so park fd 1 on stderr while the communicator is built
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.ones(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     dt = torch.bfloat16
     res = args.res

@@ -51,6 +51,7 @@ def main():
     local = int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=dev)
     cfg = StepConfig(use_cuda_graph=False)
     # (a) distributed: each rank one sample
