@@ -49,6 +49,8 @@ class LoraArena:
         for model, _ in groups:
             sites = lora_sites(model) if isinstance(model, nn.Module) else list(model)
             site_groups.append(sites)
+        if not any(site_groups):
+            raise _C.LoraB200Error("LoraArena: no LoRA sites found (inject_trainable_lora first)")
         first = next(s for sg in site_groups for s in sg)
         self.device = device or first.lora_up.weight.device
         if self.device.type != "cuda":

@@ -48,6 +48,8 @@ def _compute_dtype(x: torch.Tensor) -> torch.dtype:
     type, else bf16 (fp32 activations outside autocast: bf16 operands, fp32 accumulate/output)."""
     if x.dtype in _LOW:
         return x.dtype
+    if x.dtype != torch.float32:
+        raise LoraB200Error(f"lora_b200: unsupported activation dtype {x.dtype} (fp32, bf16, fp16 only)")
     if torch.is_autocast_enabled("cuda"):
         dt = torch.get_autocast_dtype("cuda")
         if dt in _LOW:
