@@ -188,6 +188,10 @@ class LoraArena:
                                         stream_ptr()), "lb_adamw_clip_step")
         ops._count(2)
         self.refresh_shadows()
+        # re-validate the per-site operand caches: if torch-side code edited a factor in place since
+        # the last step (version bump -> the site fell back to a private re-cast), point it back at
+        # the arena's shadow buffer, which the launch above has just refreshed
+        self._publish_shadows()
 
     def zero_grad(self):
         self.g.zero_()

@@ -412,3 +412,32 @@ def test_state_dict_and_device_moves():
     want = O.lora_linear_forward(x, sd["linear.weight"].to(torch.bfloat16), sd["linear.bias"].to(torch.bfloat16),
                                  sd["lora_down.weight"].to(torch.bfloat16), sd["lora_up.weight"].to(torch.bfloat16), 1.0)
     assert rel(y, want) < 2 ** -7
+
+
+def test_arena_step_after_torch_side_edit_keeps_operands_fresh():
+    """A factor edited in place by torch code (version bump) between two arena steps: the site
+    must see the edit immediately AND the result of the following fused optimizer step."""
+    import lora_b200 as L
+    from lora_b200.arena import LoraArena
+    from oracle import lora_ops as O
+    torch.manual_seed(0)
+    site = L.LoraInjectedLinear(320, 320, r=4, dropout_p=0.0).to(DEV)
+    site.linear.requires_grad_(False)
+    site.lora_up.weight.data.normal_(0, 0.1)
+    arena = LoraArena([([site], 1e-2)])
+    x = torch.randn(64, 320, device=DEV, dtype=torch.bfloat16)
+
+    def want():
+        return O.lora_linear_forward(x, site.linear.weight.to(torch.bfloat16), None, site.lora_down.weight,
+                                     site.lora_up.weight, 1.0)
+    assert rel(site(x), want()) < 2 ** -7
+    with torch.no_grad():
+        site.lora_up.weight.mul_(3.0)                 # torch-side in-place edit
+    assert rel(site(x), want()) < 2 ** -7
+    site.lora_up.weight.grad.normal_(0, 1.0)
+    site.lora_down.weight.grad.normal_(0, 1.0)
+    before = site.lora_up.weight.detach().clone()
+    arena.step(max_norm=0.0)
+    torch.cuda.synchronize()
+    assert not torch.equal(before, site.lora_up.weight.detach())
+    assert rel(site(x), want()) < 2 ** -7             # operands follow the fused step too
