@@ -22,6 +22,15 @@ class LoraB200Error(RuntimeError):
 
 
 def _load():
+    if not os.path.exists(LIB_PATH) and LIB_PATH == os.path.join(_HERE, "liblora_b200.so"):
+        # fresh checkout: the library is a build artefact (git-ignored). Build it once, in-tree.
+        try:
+            from .build import build
+            build()
+        except Exception as e:  # nvcc missing or compile error: there is nothing to fall back to
+            raise LoraB200Error(
+                f"{LIB_PATH} is missing and building it failed ({e}); run `python -m lora_b200.build` "
+                "(nvcc, sm_100a). lora_b200 has no fallback path.") from e
     if not os.path.exists(LIB_PATH):
         raise LoraB200Error(
             f"{LIB_PATH} is missing: build it with `python -m lora_b200.build` "
