@@ -181,7 +181,7 @@ extern "C" int lb_lora_linear_fwd_grouped(int n, const void* const* X, const voi
   if (n < 1 || n > MAX_GROUP) return LB_ERR_SHAPE;
   if (in_dtype != LB_BF16 && in_dtype != LB_F16) return LB_ERR_DTYPE;
   if (out_dtype != in_dtype && out_dtype != LB_F32) return LB_ERR_DTYPE;
-  static GroupedArgs a;   // 2.7 KB of kernel parameters; filled per call (single host thread per process)
+  GroupedArgs a = {};     // ~2.7 KB of kernel parameters (tensor maps + per-problem arguments)
   a.n_problems = n;
   long long tiles128 = 0, tiles64 = 0;
   for (int i = 0; i < n; ++i) {
