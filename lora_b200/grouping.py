@@ -43,6 +43,12 @@ class _ParentState:
         self.cache = {}      # id(site) -> (key, x kept alive, y)
         self.learned = False
 
+    def __reduce__(self):          # runtime state: copies / pickles start empty
+        return (_ParentState, ())
+
+    def __deepcopy__(self, memo):
+        return _ParentState()
+
     def finalize(self):
         by_key = {}
         for s, k in self.trace:

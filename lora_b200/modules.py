@@ -83,6 +83,17 @@ class _SiteState:
         self.grad_sink = None  # (gA view, gB view) when the arena owns the gradients
         self.parent = None     # weakref to the module this site was injected into (grouping.py)
 
+    # caches and the parent back-reference are per-process runtime state: a copied / pickled module
+    # starts with an empty one (copy.deepcopy(model), torch.save(model) keep working)
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.__init__()
+
+    def __deepcopy__(self, memo):
+        return _SiteState()
+
     def frozen(self, weight2d: torch.Tensor, dtype, need_t: bool):
         k = _key(weight2d)
         ent = self.w.get(dtype)

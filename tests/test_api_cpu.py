@@ -267,3 +267,22 @@ def test_lr_schedule_restates_diffusers_linear_and_constant():
     assert abs(d.lr_multiplier(60) - 0.5) < 1e-12 and d.lr_multiplier(110) == 0.0 and d.lr_multiplier(500) == 0.0
     d.cfg = StepConfig(lr_scheduler="constant")
     assert d.lr_multiplier(0) == 1.0 and d.lr_multiplier(10 ** 6) == 1.0
+
+
+def test_injected_model_survives_deepcopy_and_pickle(tmp_path):
+    """Runtime caches / parent back-references must not break copy.deepcopy or torch.save of a model."""
+    import copy
+    import io
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel(UNetConfig.tiny())
+    L.inject_trainable_lora_extended(unet, r=4)
+    twin = copy.deepcopy(unet)
+    a, b = _sites(unet), _sites(twin)
+    assert len(a) == len(b) and all(x is not y for x, y in zip(a, b))
+    assert all(torch.equal(x.lora_down.weight, y.lora_down.weight) for x, y in zip(a, b))
+    assert all(y._lb.parent is None and not y._lb.w for y in b)        # fresh runtime state
+    buf = io.BytesIO()
+    torch.save(unet, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert [type(m).__name__ for m in _sites(back)] == [type(m).__name__ for m in a]
