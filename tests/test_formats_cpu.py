@@ -25,24 +25,30 @@ needs_ref = pytest.mark.skipif(not os.path.exists(REF_DIR), reason="reference tr
 def _load_ref(fname, modname):
     """Load one reference file as a sub-module of a stub package `lora_diffusion` whose `.lora` is the
     real lora.py; `fire` and `diffusers` are empty stand-ins (only imported, never called here)."""
-    for stub, attrs in (("fire", {"Fire": lambda *a, **k: None}),
-                        ("diffusers", {"StableDiffusionPipeline": object})):
+    stubs = {"fire": {"Fire": lambda *a, **k: None}, "diffusers": {"StableDiffusionPipeline": object}}
+    planted = []
+    for stub, attrs in stubs.items():
         if stub not in sys.modules:
             m = types.ModuleType(stub)
             for k, v in attrs.items():
                 setattr(m, k, v)
             sys.modules[stub] = m
-    if "lora_diffusion_ref" not in sys.modules:
-        pkg = types.ModuleType("lora_diffusion_ref")
-        pkg.__path__ = [REF_DIR]
-        sys.modules["lora_diffusion_ref"] = pkg
-    full = f"lora_diffusion_ref.{modname}"
-    if full in sys.modules:
-        return sys.modules[full]
-    spec = importlib.util.spec_from_file_location(full, os.path.join(REF_DIR, fname))
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[full] = mod
-    spec.loader.exec_module(mod)
+            planted.append(stub)
+    try:
+        if "lora_diffusion_ref" not in sys.modules:
+            pkg = types.ModuleType("lora_diffusion_ref")
+            pkg.__path__ = [REF_DIR]
+            sys.modules["lora_diffusion_ref"] = pkg
+        full = f"lora_diffusion_ref.{modname}"
+        if full in sys.modules:
+            return sys.modules[full]
+        spec = importlib.util.spec_from_file_location(full, os.path.join(REF_DIR, fname))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[full] = mod
+        spec.loader.exec_module(mod)
+    finally:
+        for stub in planted:            # the stand-ins must not leak into other tests
+            sys.modules.pop(stub, None)
     return mod
 
 
@@ -231,11 +237,10 @@ def test_merge_into_pipeline_folds_the_branch_and_restores_plain_modules(tmp_pat
     assert len(changed) == sum(1 for k in t if k.startswith("unet") and k.endswith(":up"))
     # first site in injection order: W' = W + 0.5 * up @ down
     from lora_b200.inject import _find_modules
-    torch.manual_seed(0)
-    fresh = UNet2DConditionModel(UNetConfig.tiny())
+    fresh = UNet2DConditionModel(UNetConfig.tiny())          # structure only: which Linear is site 0
     parent, name, child = next(iter(_find_modules(fresh, L.UNET_DEFAULT_TARGET_REPLACE, search_class=[torch.nn.Linear])))
     full = [n for n, m in fresh.named_modules() if m is child][0]
-    want = child.weight.data + 0.5 * (t["unet:0:up"].float() @ t["unet:0:down"].float())
+    want = before[full + ".weight"] + 0.5 * (t["unet:0:up"].float() @ t["unet:0:down"].float())
     assert torch.allclose(after[full + ".weight"], want, atol=1e-6)
 
 
