@@ -34,6 +34,22 @@ def get_grouping() -> bool:
     return _ENABLED
 
 
+def link_sites(*models) -> int:
+    """(Re)attach every LoRA site of `models` to the module that holds it. Injection does this
+    itself; a `copy.deepcopy`'d or unpickled model starts without the back-references (and hence
+    runs ungrouped) until this is called. Returns the number of sites linked."""
+    import weakref
+    n = 0
+    for model in models:
+        for parent in model.modules():
+            for child in parent._modules.values():
+                if child is not None and type(child).__name__ in ("LoraInjectedLinear", "LoraInjectedConv2d") \
+                        and hasattr(child, "_lb"):
+                    child._lb.parent = weakref.ref(parent)
+                    n += 1
+    return n
+
+
 class _ParentState:
     __slots__ = ("trace", "groups", "cache", "learned")
 

@@ -62,6 +62,8 @@ class LoraTrainStep:
         self.cfg = cfg
         self.unet, self.text_encoder = unet, text_encoder
         self.device = torch.device(device or "cuda")
+        from .grouping import link_sites
+        link_sites(unet, text_encoder)       # a copied / unpickled model has lost its back-references
         groups = [(unet, cfg.learning_rate)]
         if cfg.train_text_encoder:
             groups.append((text_encoder, cfg.learning_rate_text))

@@ -281,6 +281,9 @@ def test_injected_model_survives_deepcopy_and_pickle(tmp_path):
     assert len(a) == len(b) and all(x is not y for x, y in zip(a, b))
     assert all(torch.equal(x.lora_down.weight, y.lora_down.weight) for x, y in zip(a, b))
     assert all(y._lb.parent is None and not y._lb.w for y in b)        # fresh runtime state
+    assert L.link_sites(twin) == len(b)
+    holders = {id(m) for m in twin.modules()}
+    assert all(id(y._lb.parent()) in holders and y in y._lb.parent()._modules.values() for y in b)
     buf = io.BytesIO()
     torch.save(unet, buf)
     buf.seek(0)
