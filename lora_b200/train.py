@@ -52,6 +52,10 @@ class StepConfig:
     # (mask + 0.01)^mask_temperature / max -> pred*mask, target*mask -> mse.mean([1,2,3]).mean()
     use_mask: bool = False
     mask_temperature: float = 1.0
+    # inpainting variant (cli_lora_pti.py:279-313): the UNet (in_channels = 9) sees
+    # cat([noisy latents, mask, masked-image latents], dim=1); both extra inputs are per-sample
+    # data at latent resolution, in `self.inpaint_mask` / `self.masked_latents`
+    train_inpainting: bool = False
 
 
 class LoraTrainStep:
@@ -75,6 +79,9 @@ class LoraTrainStep:
         self.input_ids = torch.zeros((latent_shape[0], seq_len), device=self.device, dtype=torch.long)
         self.loss = torch.zeros((), device=self.device, dtype=torch.float32)
         self.mask = torch.ones((latent_shape[0], 1, latent_shape[2], latent_shape[3]), device=self.device)
+        if cfg.train_inpainting:
+            self.inpaint_mask = torch.zeros((latent_shape[0], 1, latent_shape[2], latent_shape[3]), device=self.device)
+            self.masked_latents = torch.zeros(latent_shape, device=self.device, dtype=torch.float32)
         self.global_step = 0
         # pinned host mirrors for the end-to-end path
         self.h_latents = torch.zeros(latent_shape, dtype=torch.float32).pin_memory()
@@ -101,6 +108,8 @@ class LoraTrainStep:
         t_max = int(self.noiser.num_train_timesteps * cfg.t_multiplier)
         timesteps = torch.randint(0, t_max, (bsz,), device=lat.device).long()
         noisy = self.noiser.add_noise(lat, noise, timesteps)
+        if cfg.train_inpainting:
+            noisy = torch.cat([noisy, self.inpaint_mask.to(noisy.dtype), self.masked_latents.to(noisy.dtype)], dim=1)
         ac = (torch.autocast("cuda", dtype=cfg.autocast_dtype) if cfg.autocast_dtype is not None
               else torch.autocast("cuda", enabled=False))
         with ac:
@@ -126,6 +135,14 @@ class LoraTrainStep:
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)   # join: all dA/dB are in arena.g
         self.loss.copy_(loss.detach())
+
+    def set_loss_mask(self, mask_image_res: torch.Tensor):
+        """`batch["mask"]` of the PTI dataset (image resolution, [B,1,8h,8w] or anything that
+        reshapes to it) -> nearest-neighbour resize to the latent grid, as cli_lora_pti.py:342-354
+        does every step; stored in `self.mask` for `use_mask` steps."""
+        b, _, h, w = self.mask.shape
+        m = mask_image_res.to(self.device, torch.float32).reshape(b, 1, h * 8, w * 8)
+        self.mask.copy_(F.interpolate(m, size=(h, w), mode="nearest"))
 
     def _update(self):
         cfg = self.cfg

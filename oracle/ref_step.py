@@ -39,8 +39,13 @@ class RefDreamboothStep:
         unet.train()
         text_encoder.train()
 
-    def forward_loss(self, latents, input_ids, noise, timesteps):
+    def forward_loss(self, latents, input_ids, noise, timesteps, loss_mask=None, mask_temperature=1.0,
+                     inpaint=None):
+        """loss of cli_lora_pti.py:260-370 (`loss_step`, epsilon prediction, cached latents).
+        loss_mask: [B,1,8h,8w] image-resolution mask (`batch["mask"]`, :340-368) or None;
+        inpaint: (mask [B,1,h,w], masked_image_latents [B,4,h,w]) for the 9-channel UNet (:279-313)."""
         noisy = self.noiser.add_noise(latents, noise, timesteps)
+        model_in = noisy if inpaint is None else torch.cat([noisy, inpaint[0], inpaint[1]], dim=1)
         dev = latents.device.type
         ctx = torch.autocast(dev, dtype=self.autocast_dtype) if self.autocast_dtype else torch.autocast(dev, enabled=False)
         with ctx:
@@ -50,17 +55,26 @@ class RefDreamboothStep:
                 with torch.no_grad():
                     ehs = self.text_encoder(input_ids)[0]
             mdt = next(self.unet.parameters()).dtype
-            pred = self.unet(noisy.to(mdt), timesteps, ehs.to(mdt)).sample
-        return F.mse_loss(pred.float(), noise.float(), reduction="mean")
+            pred = self.unet(model_in.to(mdt), timesteps, ehs.to(mdt)).sample
+        target = noise
+        if loss_mask is not None:
+            m = loss_mask.to(pred.device).reshape(pred.shape[0], 1, pred.shape[2] * 8, pred.shape[3] * 8)
+            m = F.interpolate(m.float(), size=pred.shape[-2:], mode="nearest")
+            m = (m + 0.01).pow(mask_temperature)
+            m = m / m.max()
+            pred, target = pred * m, target * m
+            return F.mse_loss(pred.float(), target.float(), reduction="none").mean([1, 2, 3]).mean()
+        return F.mse_loss(pred.float(), target.float(), reduction="mean")
 
-    def step(self, latents, input_ids, noise=None, timesteps=None):
-        """noise/timesteps may be supplied (parity tests); otherwise drawn like the reference."""
+    def step(self, latents, input_ids, noise=None, timesteps=None, **loss_kw):
+        """noise/timesteps may be supplied (parity tests); otherwise drawn like the reference
+        (noise first, then timesteps: cli_lora_pti.py:295-304, train_lora_dreambooth.py:822-833)."""
         if noise is None:
             noise = torch.randn_like(latents)
         if timesteps is None:
             t_max = int(self.noiser.num_train_timesteps * self.t_multiplier)
             timesteps = torch.randint(0, t_max, (latents.shape[0],), device=latents.device).long()
-        loss = self.forward_loss(latents, input_ids, noise, timesteps)
+        loss = self.forward_loss(latents, input_ids, noise, timesteps, **loss_kw)
         loss.backward()
         if self.max_grad_norm:
             torch.nn.utils.clip_grad_norm_(self.unet_params + self.text_params, self.max_grad_norm)

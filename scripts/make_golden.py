@@ -14,6 +14,7 @@ Outputs (all small, committed):
                                         fixture files in /root/reference/example_loras
   golden/svd_distill.pt                 cli_svd.overwrite_base outputs on small matrices
   golden/adamw_clip.pt                  clip_grad_norm_ + torch.optim.AdamW trajectories
+  golden/pti_loss_step.pt               cli_lora_pti.loss_step losses (plain / t_mult / masked / inpainting)
 """
 import hashlib
 import importlib.util
@@ -231,6 +232,89 @@ def gen_adamw():
     torch.save(dict(p0=ps, lrs=lrs, traj=traj), f"{OUT}/adamw_clip.pt")
 
 
+def load_ref_pti(ref_lora):
+    """cli_lora_pti.py pulls diffusers / fire / the lora_diffusion package at module top; none of
+    them is touched by `loss_step` itself. Stand-ins whose attributes are inert placeholders let the
+    real file execute so that the real function object can be called."""
+    class _Inert(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return type(name, (), {})
+    saved = {}
+    # huggingface_hub is installed but no longer has the names the file asks for: shadow it too
+    for name in ("fire", "diffusers", "diffusers.optimization", "lora_diffusion", "wandb", "huggingface_hub"):
+        saved[name] = sys.modules.get(name)
+        sys.modules[name] = _Inert(name)
+    try:
+        spec = importlib.util.spec_from_file_location("ref_cli_lora_pti", f"{REF}/lora_diffusion/cli_lora_pti.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for name, old in saved.items():
+            if old is None:
+                sys.modules.pop(name, None)
+            else:
+                sys.modules[name] = old
+    return mod
+
+
+def gen_loss_step(R):
+    """The PTI/Dreambooth loss of one step, computed by the reference's own `loss_step`
+    (cli_lora_pti.py:260-370) on the tiny host models, CPU fp32, cached latents: plain, t_mutliplier
+    0.8, masked loss (two temperatures), inpainting (9-channel input), inpainting + mask."""
+    from lora_b200.host.clip import build_text_encoder
+    from lora_b200.host.ddpm import DDPMNoiser
+    from lora_b200.host.unet_sd15 import UNet2DConditionModel, UNetConfig
+    P = load_ref_pti(R)
+    noiser = DDPMNoiser(device="cpu")
+
+    class Sched:                      # what loss_step reads from a diffusers DDPMScheduler
+        config = types.SimpleNamespace(num_train_timesteps=noiser.num_train_timesteps, prediction_type="epsilon")
+        add_noise = staticmethod(noiser.add_noise)
+
+    g = torch.Generator().manual_seed(77)
+    lat = torch.randn(2, 4, 8, 8, generator=g) * 0.18215
+    ids = torch.randint(0, 1000, (2, 77), generator=g)
+    loss_mask = (torch.rand(2, 1, 64, 64, generator=g) > 0.4).float()          # image resolution
+    inp_mask = (torch.rand(2, 1, 8, 8, generator=g) > 0.5).float()             # cached: latent resolution
+    inp_lat = torch.randn(2, 4, 8, 8, generator=g) * 0.18215
+    cases = []
+    for name, in_ch, kw, with_mask in [
+            ("plain", 4, dict(), False),
+            ("t_mult_0.8", 4, dict(t_mutliplier=0.8), False),
+            ("masked_T1", 4, dict(mask_temperature=1.0), True),
+            ("masked_T2.5", 4, dict(mask_temperature=2.5), True),
+            ("inpaint", 9, dict(train_inpainting=True), False),
+            ("inpaint_masked", 9, dict(train_inpainting=True, mask_temperature=1.0), True)]:
+        torch.manual_seed(0)
+        cfg = UNetConfig.tiny()
+        cfg.in_channels = in_ch
+        unet = UNet2DConditionModel(cfg)
+        text = build_text_encoder(tiny=True)
+        # a live LoRA branch (reference modules, non-zero up) so that the loss depends on it
+        R.inject_trainable_lora(unet, r=4)
+        gg = torch.Generator().manual_seed(5)
+        for m in unet.modules():
+            if type(m).__name__ == "LoraInjectedLinear":
+                m.lora_down.weight.data.normal_(0, 0.25, generator=gg)     # explicit: independent of ctor RNG
+                m.lora_up.weight.data.normal_(0, 0.05, generator=gg)
+                m.dropout.p = 0.0
+        batch = {"pixel_values": lat, "input_ids": ids}
+        if in_ch == 9:
+            batch.update(masked_image_latents=inp_lat, mask_values=inp_mask)
+        if with_mask:
+            batch["mask"] = loss_mask
+        text.train(False), unet.train(False)
+        torch.manual_seed(1234)
+        loss = P.loss_step(batch, unet, None, text, Sched, cached_latents=True, **kw)
+        cases.append(dict(name=name, in_channels=in_ch, kwargs=kw, with_mask=with_mask, loss=float(loss)))
+    torch.save(dict(latents=lat, input_ids=ids, loss_mask=loss_mask, inpaint_mask=inp_mask,
+                    masked_latents=inp_lat, model_seed=0, up_seed=5, step_seed=1234, cases=cases),
+               f"{OUT}/pti_loss_step.pt")
+    print({c["name"]: c["loss"] for c in cases})
+
+
 if __name__ == "__main__":
     R = load_ref_lora()
     gen_ops(R)
@@ -239,5 +323,6 @@ if __name__ == "__main__":
     gen_manifest(R)
     gen_svd(R)
     gen_adamw()
+    gen_loss_step(R)
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(f"{OUT}/{fn}"))

@@ -137,3 +137,44 @@ def test_svd_oracle_vs_reference_golden():
         assert float(max(up.abs().max(), down.abs().max())) <= hi * (1 + 1e-6)
         assert float(max(c["up"].abs().max(), c["down"].abs().max())) <= hi * (1 + 1e-4)
         assert rel(up, c["up"]) < 1e-3 and rel(down, c["down"]) < 1e-3
+
+
+def test_step_loss_matches_reference_loss_step_golden():
+    """oracle/ref_step.py::RefDreamboothStep.forward_loss against losses the reference's own
+    `loss_step` (cli_lora_pti.py:260-370) produced on the same tiny models and inputs (golden
+    written by scripts/make_golden.py::gen_loss_step): plain, t_mutliplier, masked loss with two
+    temperatures, the 9-channel inpainting input, inpainting + mask. CPU fp32."""
+    import os
+    from lora_b200.host.clip import build_text_encoder
+    from lora_b200.host.ddpm import DDPMNoiser
+    from lora_b200.host.unet_sd15 import UNet2DConditionModel, UNetConfig
+    from oracle.ref_modules import ref_inject
+    from oracle.ref_step import RefDreamboothStep
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pti_loss_step.pt"))
+    lat, ids = G["latents"], G["input_ids"]
+    assert len(G["cases"]) == 6
+    for case in G["cases"]:
+        torch.manual_seed(G["model_seed"])
+        cfg = UNetConfig.tiny()
+        cfg.in_channels = case["in_channels"]
+        unet = UNet2DConditionModel(cfg)
+        text = build_text_encoder(tiny=True)
+        sites = ref_inject(unet, {"CrossAttention", "Attention", "GEGLU"}, r=4)
+        gg = torch.Generator().manual_seed(G["up_seed"])
+        for s in sites:
+            s.down.data.normal_(0, 0.25, generator=gg)
+            s.up.data.normal_(0, 0.05, generator=gg)
+        unet.train(False), text.train(False)
+        kw = case["kwargs"]
+        ref = RefDreamboothStep(unet, text, DDPMNoiser(device="cpu"), sites, None,
+                                t_multiplier=kw.get("t_mutliplier", 1.0))
+        unet.train(False), text.train(False)
+        torch.manual_seed(G["step_seed"])
+        noise = torch.randn_like(lat)                       # the reference's draw order: noise, then t
+        t = torch.randint(0, int(1000 * ref.t_multiplier), (lat.shape[0],)).long()
+        loss = ref.forward_loss(
+            lat, ids, noise, t,
+            loss_mask=G["loss_mask"] if case["with_mask"] else None,
+            mask_temperature=kw.get("mask_temperature", 1.0),
+            inpaint=(G["inpaint_mask"], G["masked_latents"]) if kw.get("train_inpainting") else None)
+        assert abs(float(loss) - case["loss"]) <= 2e-6 * abs(case["loss"]), (case["name"], float(loss), case["loss"])
