@@ -4,7 +4,7 @@ PyTorch-eager restatement of the reference's LoRA operator modules and of its si
 used (a) as the CPU baseline timed beside the CUDA kernels (bench.py --impl reference /
 cpu_baseline) and (b) as the module-level parity target on the GPU box, where /root/reference
 does not exist. Checked against the real /root/reference/lora_diffusion/lora.py in
-tests/test_oracle_vs_reference.py (runs wherever the reference tree is mounted) and through
+tests/test_vs_reference_live.py (runs wherever the reference tree is mounted) and through
 the golden vectors it generated (tests/golden/, scripts/make_golden.py).
 
 Written functionally (F.linear / F.conv2d on explicit Parameters) rather than as the

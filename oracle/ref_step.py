@@ -5,6 +5,11 @@ Restates training_scripts/train_lora_dreambooth.py:651-676 (AdamW param groups) 
 torch.nn.utils.clip_grad_norm_, F.mse_loss -- over RefLoraSite modules (oracle/ref_modules.py).
 The host UNet / text encoder / noiser objects are passed in by the caller (tests, bench.py);
 this file imports nothing from the product package.
+
+Pinned: `forward_loss` reproduces the losses of the reference's own `loss_step`
+(lora_diffusion/cli_lora_pti.py:260-370; plain, t_mutliplier, masked, inpainting) to 2e-6 relative
+-- tests/golden/pti_loss_step.pt, written by scripts/make_golden.py::gen_loss_step, checked in
+tests/test_oracle_golden.py; the clip + AdamW trajectory is pinned by tests/golden/adamw_clip.pt.
 """
 import itertools
 from typing import List, Optional

@@ -15,9 +15,11 @@ Outputs (all small, committed):
   golden/svd_distill.pt                 cli_svd.overwrite_base outputs on small matrices
   golden/adamw_clip.pt                  clip_grad_norm_ + torch.optim.AdamW trajectories
   golden/pti_loss_step.pt               cli_lora_pti.loss_step losses (plain / t_mult / masked / inpainting)
+  golden/ti_train_inversion.pt          cli_lora_pti.train_inversion: 3 real steps (grads, lr, rows after)
 """
 import hashlib
 import importlib.util
+import itertools
 import json
 import os
 import sys
@@ -315,6 +317,75 @@ def gen_loss_step(R):
     print({c["name"]: c["loss"] for c in cases})
 
 
+def gen_ti(R):
+    """Textual-inversion phase: the reference's own `train_inversion` loop (cli_lora_pti.py:373-542)
+    run for 3 steps on the tiny models, CPU fp32, with torch.optim.AdamW over the embedding table
+    built as at :889-895 and a LambdaLR warm-up so that the learning rate (and the norm-decay
+    lambda that follows it, :456) changes every step. Recorded: per step the gradient rows of the
+    placeholder tokens, the lr in force, and the placeholder rows + whole-table sum afterwards."""
+    from lora_b200.host.clip import build_text_encoder
+    from lora_b200.host.ddpm import DDPMNoiser
+    from lora_b200.host.unet_sd15 import UNet2DConditionModel, UNetConfig
+    P = load_ref_pti(R)
+    noiser = DDPMNoiser(device="cpu")
+
+    class Sched:
+        config = types.SimpleNamespace(num_train_timesteps=noiser.num_train_timesteps, prediction_type="epsilon")
+        add_noise = staticmethod(noiser.add_noise)
+
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel(UNetConfig.tiny())
+    text = build_text_encoder(tiny=True)
+    unet.requires_grad_(False)
+    for prm in itertools.chain(text.text_model.encoder.parameters(), text.text_model.final_layer_norm.parameters(),
+                               text.text_model.embeddings.position_embedding.parameters()):
+        prm.requires_grad = False
+    emb = text.get_input_embeddings()
+    V, D = emb.weight.shape
+    tok = [V - 2, V - 1]
+    index_no_updates = torch.arange(V) != -1
+    for t in tok:
+        index_no_updates[t] = False
+    g = torch.Generator().manual_seed(21)
+    batches = []
+    for _ in range(3):
+        ids = torch.randint(0, V - 2, (2, 77), generator=g)
+        ids[0, 5], ids[1, 9], ids[1, 10] = tok[0], tok[1], tok[0]
+        batches.append({"pixel_values": torch.randn(2, 4, 8, 8, generator=g) * 0.18215, "input_ids": ids})
+    base_lr, wd = 5e-3, 1e-2
+    steps = []
+
+    class Recording(torch.optim.AdamW):
+        def step(self, closure=None):
+            steps.append(dict(grad_rows=emb.weight.grad[tok].detach().clone(), lr=self.param_groups[0]["lr"]))
+            return super().step(closure)
+
+    opt = Recording(emb.parameters(), lr=base_lr, betas=(0.9, 0.999), eps=1e-08, weight_decay=wd)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda k: min(1.0, (k + 1) / 4))
+
+    class Snap:                     # lr_scheduler as train_inversion uses it; snapshots the table it finds
+        def step(self_inner):
+            if steps:
+                steps[-1].update(rows_after=emb.weight.data[tok].clone(), table_sum=float(emb.weight.data.double().sum()))
+            sched.step()
+
+        def get_last_lr(self_inner):
+            return sched.get_last_lr()
+
+    table0_rows = emb.weight.data[tok].clone()
+    table0_sum = float(emb.weight.data.double().sum())
+    torch.manual_seed(4321)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        P.train_inversion(unet, None, text, batches, 3, Sched, index_no_updates, opt, 10 ** 9, tok, ["<a>", "<b>"],
+                          "/nonexistent", None, Snap(), "/nonexistent", True, clip_ti_decay=True)
+    steps[-1].update(rows_after=emb.weight.data[tok].clone(), table_sum=float(emb.weight.data.double().sum()))
+    assert len(steps) == 3 and all("rows_after" in s for s in steps)
+    torch.save(dict(model_seed=0, token_ids=tok, base_lr=base_lr, weight_decay=wd, table0_rows=table0_rows,
+                    table0_sum=table0_sum, steps=steps), f"{OUT}/ti_train_inversion.pt")
+    print("ti lrs", [s["lr"] for s in steps], "row norms", [s["rows_after"].norm(dim=-1).tolist() for s in steps])
+
+
 if __name__ == "__main__":
     R = load_ref_lora()
     gen_ops(R)
@@ -324,5 +395,6 @@ if __name__ == "__main__":
     gen_svd(R)
     gen_adamw()
     gen_loss_step(R)
+    gen_ti(R)
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(f"{OUT}/{fn}"))

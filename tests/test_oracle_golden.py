@@ -178,3 +178,35 @@ def test_step_loss_matches_reference_loss_step_golden():
             mask_temperature=kw.get("mask_temperature", 1.0),
             inpaint=(G["inpaint_mask"], G["masked_latents"]) if kw.get("train_inpainting") else None)
         assert abs(float(loss) - case["loss"]) <= 2e-6 * abs(case["loss"]), (case["name"], float(loss), case["loss"])
+
+
+def test_ti_oracle_matches_reference_train_inversion_golden():
+    """oracle/ti_ref.py::ti_table_step replayed over the gradients the reference's own
+    `train_inversion` loop (cli_lora_pti.py:373-542) saw for 3 steps (golden from
+    scripts/make_golden.py::gen_ti: per-step placeholder-row gradients, the scheduled lr, rows and
+    table sum afterwards): trained rows equal after every step, every other row restored."""
+    import os
+    from lora_b200.host.clip import build_text_encoder
+    from lora_b200.host.unet_sd15 import UNet2DConditionModel, UNetConfig
+    from oracle.ti_ref import ti_table_step
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ti_train_inversion.pt"))
+    torch.manual_seed(G["model_seed"])
+    UNet2DConditionModel(UNetConfig.tiny())              # consumes the RNG exactly as the generator did
+    te = build_text_encoder(tiny=True)
+    table0 = te.get_input_embeddings().weight.detach().clone()
+    tok = G["token_ids"]
+    assert torch.equal(table0[tok], G["table0_rows"]) and abs(float(table0.double().sum()) - G["table0_sum"]) < 1e-9
+    V, D = table0.shape
+    upd = torch.zeros(V, dtype=torch.bool)
+    upd[tok] = True
+    table, m, v = table0.clone(), torch.zeros(V, D), torch.zeros(V, D)
+    for k, st in enumerate(G["steps"], start=1):
+        dense = torch.zeros(V, D)
+        dense[tok] = st["grad_rows"]
+        table, m, v = ti_table_step(table, dense, m, v, k, st["lr"], upd, table0,
+                                    weight_decay=G["weight_decay"], clip_ti_decay=True)
+        want = st["rows_after"].double()
+        assert float((table[tok] - want).norm() / want.norm()) < 2e-6, k
+        assert torch.equal(table[~upd], table0[~upd].double())
+        assert abs(float(table.sum()) - st["table_sum"]) < 1e-4
+    assert G["steps"][0]["lr"] != G["steps"][2]["lr"]       # the schedule really moved the lr / lambda
