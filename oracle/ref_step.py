@@ -9,7 +9,10 @@ this file imports nothing from the product package.
 Pinned: `forward_loss` reproduces the losses of the reference's own `loss_step`
 (lora_diffusion/cli_lora_pti.py:260-370; plain, t_mutliplier, masked, inpainting) to 2e-6 relative
 -- tests/golden/pti_loss_step.pt, written by scripts/make_golden.py::gen_loss_step, checked in
-tests/test_oracle_golden.py; the clip + AdamW trajectory is pinned by tests/golden/adamw_clip.pt.
+tests/test_oracle_golden.py; `step` reproduces 3 iterations of the reference's real
+`perform_tuning` loop (cli_lora_pti.py:545-680: per-step loss to 5e-6, every LoRA factor afterwards
+to 2e-7 -- tests/golden/pti_perform_tuning.pt, gen_tuning); the clip + AdamW trajectory alone is
+also pinned by tests/golden/adamw_clip.pt.
 """
 import itertools
 from typing import List, Optional

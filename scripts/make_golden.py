@@ -16,6 +16,7 @@ Outputs (all small, committed):
   golden/adamw_clip.pt                  clip_grad_norm_ + torch.optim.AdamW trajectories
   golden/pti_loss_step.pt               cli_lora_pti.loss_step losses (plain / t_mult / masked / inpainting)
   golden/ti_train_inversion.pt          cli_lora_pti.train_inversion: 3 real steps (grads, lr, rows after)
+  golden/pti_perform_tuning.pt          cli_lora_pti.perform_tuning: 3 real steps (losses, lrs, all factors after)
 """
 import hashlib
 import importlib.util
@@ -242,7 +243,7 @@ def load_ref_pti(ref_lora):
         def __getattr__(self, name):
             if name.startswith("__"):
                 raise AttributeError(name)
-            return type(name, (), {})
+            return type(name, (), {"__init__": lambda self, *a, **k: None})
     saved = {}
     # huggingface_hub is installed but no longer has the names the file asks for: shadow it too
     for name in ("fire", "diffusers", "diffusers.optimization", "lora_diffusion", "wandb", "huggingface_hub"):
@@ -386,6 +387,83 @@ def gen_ti(R):
     print("ti lrs", [s["lr"] for s in steps], "row norms", [s["rows_after"].norm(dim=-1).tolist() for s in steps])
 
 
+def gen_tuning(R):
+    """LoRA-tuning phase: the reference's own `perform_tuning` loop (cli_lora_pti.py:545-680) for 3
+    steps, CPU fp32 (its `torch.cuda.amp.autocast()` is inert without CUDA), on the tiny UNet + text
+    encoder injected by the reference's `inject_trainable_lora` (r=4), AdamW param groups built as
+    at :958-997 (unet_lr 1e-4 / text_encoder_lr 1e-5, weight_decay_lora 1e-3), a LambdaLR linear
+    decay. Every factor is set from a seeded generator first, so the trajectory depends on no
+    constructor RNG. Recorded: per-step loss and lr, and every factor after the 3 steps."""
+    from lora_b200.host.clip import build_text_encoder
+    from lora_b200.host.ddpm import DDPMNoiser
+    from lora_b200.host.unet_sd15 import UNet2DConditionModel, UNetConfig
+    P = load_ref_pti(R)
+    noiser = DDPMNoiser(device="cpu")
+
+    class Sched:
+        config = types.SimpleNamespace(num_train_timesteps=noiser.num_train_timesteps, prediction_type="epsilon")
+        add_noise = staticmethod(noiser.add_noise)
+
+    torch.manual_seed(0)
+    unet = UNet2DConditionModel(UNetConfig.tiny())
+    text = build_text_encoder(tiny=True)
+    unet.requires_grad_(False)
+    text.requires_grad_(False)
+    up, _ = R.inject_trainable_lora(unet, r=4)
+    tp, _ = R.inject_trainable_lora(text, target_replace_module={"CLIPAttention"}, r=4)
+    gg = torch.Generator().manual_seed(6)
+    sites = [m for m in list(unet.modules()) + list(text.modules()) if type(m).__name__ == "LoraInjectedLinear"]
+    for m in sites:
+        m.lora_down.weight.data.normal_(0, 0.25, generator=gg)
+        m.lora_up.weight.data.normal_(0, 0.05, generator=gg)
+    opt = torch.optim.AdamW([{"params": itertools.chain(*up), "lr": 1e-4},
+                             {"params": itertools.chain(*tp), "lr": 1e-5}], weight_decay=1e-3)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda k: max(0.0, 1.0 - k / 6))
+    g = torch.Generator().manual_seed(22)
+    V = text.get_input_embeddings().weight.shape[0]
+    batches = [{"pixel_values": torch.randn(2, 4, 8, 8, generator=g) * 0.18215,
+                "input_ids": torch.randint(0, V, (2, 77), generator=g),
+                "mask": (torch.rand(2, 1, 64, 64, generator=g) > 0.4).float()} for _ in range(3)]
+    rec = []
+
+    class Recording:
+        def step(self_inner):
+            sched.step()
+            rec.append(dict(lrs=[grp["lr"] for grp in opt.param_groups]))
+
+        def get_last_lr(self_inner):
+            return sched.get_last_lr()
+
+    real_loss_step = P.loss_step
+
+    def spy(*a, **k):
+        out = real_loss_step(*a, **k)
+        rec[-1]["loss"] = float(out.detach())
+        rec[-1]["kwargs"] = {kk: vv for kk, vv in k.items() if isinstance(vv, (int, float, bool))}
+        return out
+
+    P.loss_step = spy
+    torch.manual_seed(999)
+    import contextlib, io
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            P.perform_tuning(unet, None, text, batches, 3, Sched, opt, 10 ** 9, [], [], "/nonexistent",
+                             Recording(), {"CrossAttention", "Attention", "GEGLU"}, {"CLIPAttention"}, 1.0,
+                             "out", None, "/nonexistent", True)
+    finally:
+        P.loss_step = real_loss_step
+    assert len(rec) == 3 and rec[0]["kwargs"]["t_mutliplier"] == 0.8
+    keep = sorted({0, 1, 2, len(up) // 2 - 1, len(up) // 2, len(sites) - 1})      # a few sites in full ...
+    factors = {i: (sites[i].lora_up.weight.detach().clone(), sites[i].lora_down.weight.detach().clone()) for i in keep}
+    sums = [(float(m.lora_up.weight.double().sum()), float(m.lora_down.weight.double().sum()),     # ... all by moments
+             float((m.lora_up.weight.double() ** 2).sum()), float((m.lora_down.weight.double() ** 2).sum())) for m in sites]
+    for b in batches:
+        b["mask"] = b["mask"].bool()
+    torch.save(dict(model_seed=0, factor_seed=6, step_seed=999, n_unet_sites=len(up) // 2, batches=batches,
+                    steps=rec, factors=factors, factor_moments=sums), f"{OUT}/pti_perform_tuning.pt")
+    print("tuning", [(r["loss"], r["lrs"]) for r in rec], len(sites))
+
+
 if __name__ == "__main__":
     R = load_ref_lora()
     gen_ops(R)
@@ -396,5 +474,6 @@ if __name__ == "__main__":
     gen_adamw()
     gen_loss_step(R)
     gen_ti(R)
+    gen_tuning(R)
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(f"{OUT}/{fn}"))

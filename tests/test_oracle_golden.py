@@ -210,3 +210,44 @@ def test_ti_oracle_matches_reference_train_inversion_golden():
         assert torch.equal(table[~upd], table0[~upd].double())
         assert abs(float(table.sum()) - st["table_sum"]) < 1e-4
     assert G["steps"][0]["lr"] != G["steps"][2]["lr"]       # the schedule really moved the lr / lambda
+
+
+def test_oracle_step_matches_reference_perform_tuning_golden():
+    """oracle/ref_step.py::RefDreamboothStep.step (noise, t < 0.8*T, masked loss, backward,
+    clip_grad_norm_(1.0) over all parameters, two-group AdamW) against 3 iterations of the
+    reference's real `perform_tuning` loop (cli_lora_pti.py:545-680; golden from
+    scripts/make_golden.py::gen_tuning): per-step loss and every LoRA factor afterwards."""
+    import os
+    from lora_b200.host.clip import build_text_encoder
+    from lora_b200.host.ddpm import DDPMNoiser
+    from lora_b200.host.unet_sd15 import UNet2DConditionModel, UNetConfig
+    from oracle.ref_modules import ref_inject
+    from oracle.ref_step import RefDreamboothStep
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pti_perform_tuning.pt"))
+    torch.manual_seed(G["model_seed"])
+    unet = UNet2DConditionModel(UNetConfig.tiny())
+    text = build_text_encoder(tiny=True)
+    us = ref_inject(unet, {"CrossAttention", "Attention", "GEGLU"}, r=4)
+    ts = ref_inject(text, {"CLIPAttention"}, r=4)
+    assert len(us) == G["n_unet_sites"] and len(us) + len(ts) == len(G["factor_moments"])
+    gg = torch.Generator().manual_seed(G["factor_seed"])
+    for s in us + ts:
+        s.down.data.normal_(0, 0.25, generator=gg)
+        s.up.data.normal_(0, 0.05, generator=gg)
+    ref = RefDreamboothStep(unet, text, DDPMNoiser(device="cpu"), us, ts, lr=1e-4, lr_text=1e-5,
+                            weight_decay=1e-3, t_multiplier=0.8)
+    torch.manual_seed(G["step_seed"])
+    for st, batch in zip(G["steps"], G["batches"]):
+        for grp, lr in zip(ref.opt.param_groups, st["lrs"]):
+            grp["lr"] = lr                                   # lr_scheduler.step() precedes the update
+        loss = ref.step(batch["pixel_values"], batch["input_ids"], loss_mask=batch["mask"].float(),
+                        mask_temperature=st["kwargs"]["mask_temperature"])
+        assert abs(float(loss) - st["loss"]) <= 5e-6 * abs(st["loss"]), (float(loss), st["loss"])
+    sites = us + ts
+    for i, (up, down) in G["factors"].items():
+        assert torch.allclose(sites[i].up.data, up, rtol=0, atol=2e-7), i
+        assert torch.allclose(sites[i].down.data, down, rtol=0, atol=2e-7), i
+    for s, (su, sd, qu, qd) in zip(sites, G["factor_moments"]):
+        assert abs(float(s.up.data.double().sum()) - su) < 1e-5 and abs(float(s.down.data.double().sum()) - sd) < 1e-5
+        assert abs(float((s.up.data.double() ** 2).sum()) - qu) < 1e-5 * max(1.0, qu)
+        assert abs(float((s.down.data.double() ** 2).sum()) - qd) < 1e-5 * max(1.0, qd)
