@@ -3,6 +3,7 @@
 // part of its autograd backward. Kernel: fused_core.cuh.
 #include "fused_core.cuh"
 #include "fused_persistent.cuh"
+#include "fused_splitk.cuh"
 #include "lora_b200.h"
 #include "tmap.h"
 
@@ -91,6 +92,41 @@ static int launch_grouped(GroupedArgs& a, const void* const* X, const void* cons
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }
 
+
+// EXPERIMENTAL cluster split-K schedule (fused_splitk.cuh): SPLIT CTAs of one cluster per output tile.
+template <int BLOCK_N, int STAGES, typename OutT, int SPLIT>
+static int launch_splitk(const void* X, const void* W, const void* Dn, void* Y, const FusedParams& p,
+                         int out_dtype, cudaStream_t stream) {
+  using S = SplitSmem<BLOCK_N, STAGES, OutT, SPLIT>;
+  auto kern = fused_lora_splitk_kernel<BLOCK_N, STAGES, OutT, SPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES) != cudaSuccess)
+      return LB_ERR_CUDA;
+    attr_set = true;
+  }
+  const CUtensorMapDataType in_dt = p.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
+  CUtensorMap tmX, tmW, tmD, tmY;
+  if (!tmap_2d(&tmX, X, in_dt, 2, p.K, p.M, BLOCK_K, BLOCK_M, true)) return LB_ERR_TMAP;
+  if (!tmap_2d(&tmW, W, in_dt, 2, p.K, p.N, BLOCK_K, BLOCK_N, true)) return LB_ERR_TMAP;
+  if (!tmap_2d(&tmD, Dn, in_dt, 2, p.K, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
+  if (!tmap_2d(&tmY, Y, out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M, SPLIT);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = S::DYN_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = SPLIT;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, tmX, tmW, tmD, tmY, p) == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
 static int g_linear_mode = 0;
 static unsigned long long* g_dbg = nullptr;  // profiling: device buffer of 16 timestamps  // 0 = auto, 1 = one tile per CTA (2-3 CTAs/SM), 2 = persistent
 
@@ -98,7 +134,9 @@ static unsigned long long* g_dbg = nullptr;  // profiling: device buffer of 16 t
 
 // Tuning knob (benchmarks / profiling only): force the tile schedule of lb_lora_linear_fwd.
 extern "C" int lb_debug_set_linear_mode(int mode) {
-  if (mode < 0 || mode > 11) return LB_ERR_SHAPE;   // schedule + 4 * block_n choice (0 auto, 1: 64, 2: 128)
+  // schedule (0 auto, 1 one tile per CTA, 2 persistent, 3 EXPERIMENTAL cluster split-K)
+  // + 4 * block_n choice (0 auto, 1: 64, 2: 128) + 16 * split-K factor choice (0: auto, 1..3: 2..4 CTAs)
+  if (mode < 0 || mode > 63 || ((mode >> 2) & 3) == 3) return LB_ERR_SHAPE;
   lb::g_linear_mode = mode;
   return LB_OK;
 }
@@ -135,7 +173,7 @@ extern "C" int lb_lora_linear_fwd(const void* X, const void* W, const float* bia
   p.fmt = (in_dtype == LB_BF16) ? 1 : 0; p.t_group = 0; p.dbg = g_dbg;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
-  const int sched = g_linear_mode & 3, bn_choice = g_linear_mode >> 2;
+  const int sched = g_linear_mode & 3, bn_choice = (g_linear_mode >> 2) & 3, split_choice = g_linear_mode >> 4;
   const long long tiles128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
   bool narrow = tiles128 < 120;  // not enough 128-wide tiles to fill 148 SMs: halve BLOCK_N
   if (K >= 2048 && tiles128 >= 64) narrow = false;  // long K: per-tile work is large, keep W reuse
@@ -144,6 +182,24 @@ extern "C" int lb_lora_linear_fwd(const void* X, const void* W, const float* bia
   // More tiles than SMs: persistent CTAs with a double-buffered TMEM accumulator (epilogue of
   // tile i overlaps the main loop of tile i+1). Otherwise one tile per CTA.
   const long long tiles_n = narrow ? static_cast<long long>((M + 127) / 128) * ((N + 63) / 64) : tiles128;
+  if (sched == 3 && T_in == nullptr) {
+    // EXPERIMENTAL, opt-in only: split the K loop of every tile across a cluster of 2..4 CTAs
+    const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    int split = split_choice ? split_choice + 1 : 4;
+    if (split > num_kb) split = num_kb;
+    if (bn_choice == 2 && split > 2) split = 2;        // 128-wide partials: one peer slot fits
+    if (split >= 2) {
+      if (out_dtype == LB_F32) {
+        if (split == 2) return launch_splitk<64, 4, float, 2>(X, W, down16, Y, p, out_dtype, st);
+        if (split == 3) return launch_splitk<64, 3, float, 3>(X, W, down16, Y, p, out_dtype, st);
+        return launch_splitk<64, 2, float, 4>(X, W, down16, Y, p, out_dtype, st);
+      }
+      if (bn_choice == 2) return launch_splitk<128, 3, uint16_t, 2>(X, W, down16, Y, p, out_dtype, st);
+      if (split == 2) return launch_splitk<64, 6, uint16_t, 2>(X, W, down16, Y, p, out_dtype, st);
+      if (split == 3) return launch_splitk<64, 4, uint16_t, 3>(X, W, down16, Y, p, out_dtype, st);
+      return launch_splitk<64, 3, uint16_t, 4>(X, W, down16, Y, p, out_dtype, st);
+    }
+  }
   const bool persistent = sched == 2 || (sched == 0 && tiles_n >= 3 * 148);
   if (persistent) {
     if (out_dtype == LB_F32) {
