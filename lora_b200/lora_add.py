@@ -2,7 +2,7 @@
 
 Mirrors `lora_diffusion/cli_lora_add.py:24-183` of the reference, modes
   lpl          LoRA (+) LoRA: alpha_1 * factors_1 + alpha_2 * factors_2, `.pt` pair lists or safetensors
-  ljl          join: rank-concatenate two safetensors LoRAs (`lora_manager.lora_join`)
+  ljl          join: rank-concatenate two safetensors LoRAs (`join.lora_join`)
   upl          pipeline (+) LoRA: W += alpha_1 * B·A on every site, LoRA removed, pipeline saved
   upl-ckpt-v2  the same, then exported as a CompVis `.ckpt` + an A1111 textual-inversion `.pt`
 
@@ -18,7 +18,7 @@ from typing import Callable, Optional
 
 import torch
 
-from .lora_manager import lora_join
+from .join import lora_join
 from .patch import collapse_lora, monkeypatch_remove_lora, patch_pipe
 from .persist import _text_lora_path
 

@@ -1,40 +1,50 @@
-"""`.pt` LoRA / textual-inversion files -> one `.safetensors` LoRA file.
+"""Pack `.pt` LoRA pair lists and textual-inversion `.pt` dicts into ONE `.safetensors` file
+(behaviour of the reference's `cli_pt_to_safetensors.convert`, :19-77).
 
-Mirrors `lora_diffusion/cli_pt_to_safetensors.py:19-77` of the reference.
-A `.pt` that unpickles to a dict is a token -> embedding table; anything else is a LoRA pair list
-[up, down, up, down, ...] whose model name is the second-to-last dotted part of the file name
-(`x.text_encoder.pt` -> text_encoder, `x.pt` -> unet). Per-model overrides come as keyword
-arguments `"<name>.rank"`, `"<name>.target_modules"`.
+File kinds are told apart by what unpickles: a dict is a {token: embedding} table, anything else
+is the flat list [up_0, down_0, up_1, down_1, ...] that `save_lora_weight` writes. The model a
+list belongs to is read off the file name -- `<stem>.<model>.pt`, plain `<stem>.pt` meaning the
+UNet. Keyword arguments of the form `"<model>.rank"` / `"<model>.target_modules"` override the
+defaults (rank 4, the model's default target set).
 """
 import os
+from typing import Dict, Tuple
 
 import torch
 
-from .inject import (DEFAULT_TARGET_REPLACE, TEXT_ENCODER_DEFAULT_TARGET_REPLACE,
-                     UNET_DEFAULT_TARGET_REPLACE)
+from . import inject as _inject
 from .persist import convert_loras_to_safeloras_with_embeds
-
-_TARGETS = {"unet": UNET_DEFAULT_TARGET_REPLACE, "text_encoder": TEXT_ENCODER_DEFAULT_TARGET_REPLACE}
 
 
 def model_name_of(path: str) -> str:
-    parts = os.path.basename(path).split(".")
-    return parts[-2] if len(parts) > 2 else "unet"
+    pieces = os.path.basename(path).split(".")
+    return "unet" if len(pieces) <= 2 else pieces[-2]
+
+
+def _defaults_for(model: str) -> Dict[str, object]:
+    targets = {"unet": _inject.UNET_DEFAULT_TARGET_REPLACE,
+               "text_encoder": _inject.TEXT_ENCODER_DEFAULT_TARGET_REPLACE}.get(model, _inject.DEFAULT_TARGET_REPLACE)
+    return {"target_modules": targets, "rank": 4}
+
+
+def _overrides_for(model: str, settings: Dict[str, object]) -> Dict[str, object]:
+    lead = model + "."
+    return {key[len(lead):]: value for key, value in settings.items() if key.startswith(lead)}
 
 
 def convert(*paths, outpath, overwrite=False, **settings):
-    if os.path.exists(outpath) and not overwrite:
+    if not overwrite and os.path.exists(outpath):
         raise ValueError(f"Output path {outpath} already exists, and overwrite is not True")
-    modelmap, embeds = {}, {}
+    embeds: Dict[str, torch.Tensor] = {}
+    modelmap: Dict[str, Tuple[str, object, int]] = {}
     for path in paths:
-        data = torch.load(path)
-        if isinstance(data, dict):
-            print(f"Loading textual inversion embeds {data.keys()} from {path}")
-            embeds.update(data)
-            continue
-        name = model_name_of(path)
-        cfg = {"target_modules": _TARGETS.get(name, DEFAULT_TARGET_REPLACE), "rank": 4}
-        cfg.update({k[len(name) + 1:]: v for k, v in settings.items() if k.startswith(name + ".")})
-        print(f"Loading Lora for {name} from {path} with settings {cfg}")
-        modelmap[name] = (path, cfg["target_modules"], cfg["rank"])
+        payload = torch.load(path)
+        if isinstance(payload, dict):
+            print(f"Loading textual inversion embeds {payload.keys()} from {path}")
+            embeds.update(payload)
+        else:
+            model = model_name_of(path)
+            opts = {**_defaults_for(model), **_overrides_for(model, settings)}
+            print(f"Loading Lora for {model} from {path} with settings {opts}")
+            modelmap[model] = (path, opts["target_modules"], opts["rank"])
     convert_loras_to_safeloras_with_embeds(modelmap, embeds, outpath)
