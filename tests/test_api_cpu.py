@@ -289,3 +289,63 @@ def test_injected_model_survives_deepcopy_and_pickle(tmp_path):
     buf.seek(0)
     back = torch.load(buf, weights_only=False)
     assert [type(m).__name__ for m in _sites(back)] == [type(m).__name__ for m in a]
+
+
+@pytest.mark.parametrize("inpaint,masked", [(False, False), (False, True), (True, False), (True, True)])
+def test_train_step_forward_backward_body_on_cpu_doubles(inpaint, masked):
+    """lora_b200.train.LoraTrainStep._fwd_bwd (noise draw, t_multiplier, inpainting concat, masked
+    loss, set_loss_mask's resize) exercised WITHOUT a GPU: the object is assembled by hand around
+    CPU host models whose LoRA sites are the oracle's eager modules (the product's own modules have
+    no CPU path), and its loss is compared with oracle/ref_step.py -- itself pinned to the
+    reference's `loss_step` -- for the same seed. Covers the Python of the step engine that the
+    GPU-only tests would otherwise be the first to execute."""
+    from lora_b200.host.clip import build_text_encoder
+    from lora_b200.host.ddpm import DDPMNoiser
+    from lora_b200.train import LoraTrainStep, StepConfig
+    from oracle.ref_modules import ref_inject
+    from oracle.ref_step import RefDreamboothStep
+    torch.manual_seed(0)
+    cfg_u = UNetConfig.tiny()
+    cfg_u.in_channels = 9 if inpaint else 4
+    unet, text = UNet2DConditionModel(cfg_u), build_text_encoder(tiny=True)
+    us = ref_inject(unet, {"CrossAttention", "Attention", "GEGLU"}, r=4)
+    ts = ref_inject(text, {"CLIPAttention"}, r=4)
+    g = torch.Generator().manual_seed(1)
+    for s in us + ts:
+        s.up.data.normal_(0, 0.05, generator=g)
+    shape = (2, 4, 8, 8)
+    tr = object.__new__(LoraTrainStep)              # no arena / CUDA buffers: only what _fwd_bwd touches
+    tr.cfg = StepConfig(use_cuda_graph=False, t_multiplier=0.8, use_mask=masked, mask_temperature=2.0,
+                        train_inpainting=inpaint)
+    tr.unet, tr.text_encoder, tr.device = unet, text, torch.device("cpu")
+    tr.noiser, tr.model_dtype, tr._side = DDPMNoiser(device="cpu"), torch.float32, None
+    tr.latents = torch.randn(shape, generator=g) * 0.18215
+    tr.input_ids = torch.randint(0, 1000, (2, 77), generator=g)
+    tr.loss = torch.zeros(())
+    tr.mask = torch.ones(2, 1, 8, 8)
+    kw = {}
+    if masked:
+        img_mask = (torch.rand(2, 1, 64, 64, generator=g) > 0.4).float()
+        tr.set_loss_mask(img_mask)
+        kw.update(loss_mask=img_mask, mask_temperature=2.0)
+    if inpaint:
+        tr.inpaint_mask = (torch.rand(2, 1, 8, 8, generator=g) > 0.5).float()
+        tr.masked_latents = torch.randn(shape, generator=g) * 0.18215
+        kw.update(inpaint=(tr.inpaint_mask, tr.masked_latents))
+    ref = RefDreamboothStep(unet, text, DDPMNoiser(device="cpu"), us, ts, t_multiplier=0.8)
+    torch.manual_seed(77)
+    noise = torch.randn(shape)
+    t = torch.randint(0, 800, (2,)).long()
+    want = ref.forward_loss(tr.latents, tr.input_ids, noise, t, **kw)
+    want.backward()
+    g_ref = torch.cat([p.grad.flatten() for p in ref.unet_params + ref.text_params])
+    ref.opt.zero_grad()
+    torch.manual_seed(77)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")             # torch.autocast("cuda", enabled=False) on a CPU-only box
+        tr._fwd_bwd()
+    g_ours = torch.cat([p.grad.flatten() for p in ref.unet_params + ref.text_params])
+    assert abs(float(tr.loss) - float(want)) <= 1e-5 * abs(float(want))
+    # channels_last input on our side: a different (equally valid) fp32 convolution order
+    assert float((g_ours - g_ref).norm() / g_ref.norm()) < 1e-4
