@@ -48,6 +48,11 @@ class StepConfig:
     lr_scheduler: str = "constant"
     lr_warmup_steps: int = 0
     max_train_steps: int = 1000
+    # The two trainers advance the schedule at different points: train_lora_dreambooth.py:886 calls
+    # lr_scheduler.step() AFTER optimizer.step() (iteration k, 0-based, runs at lambda(k));
+    # cli_lora_pti.py:587 (perform_tuning) and :417 (train_inversion) call it FIRST (iteration k runs
+    # at lambda(k + 1)). True selects the PTI order.
+    lr_step_first: bool = False
     # PTI masked loss (cli_lora_pti.py:340-368): mask (latent resolution, in `self.mask`) ->
     # (mask + 0.01)^mask_temperature / max -> pred*mask, target*mask -> mse.mean([1,2,3]).mean()
     use_mask: bool = False
@@ -199,7 +204,8 @@ class LoraTrainStep:
     def step_device(self) -> torch.Tensor:
         """One step on inputs already resident in self.latents / self.input_ids."""
         if self.cfg.lr_scheduler != "constant" or self.cfg.lr_warmup_steps > 0:
-            mult = self.lr_multiplier(self.global_step)      # host-side schedule, tiny async H2D copy
+            k = self.global_step + (1 if self.cfg.lr_step_first else 0)
+            mult = self.lr_multiplier(k)                     # host-side schedule, tiny async H2D copy
             self.arena.set_lr([b * mult for b in self.arena.base_lr])
         self.global_step += 1
         if self.graph is not None:

@@ -349,3 +349,32 @@ def test_train_step_forward_backward_body_on_cpu_doubles(inpaint, masked):
     assert abs(float(tr.loss) - float(want)) <= 1e-5 * abs(float(want))
     # channels_last input on our side: a different (equally valid) fp32 convolution order
     assert float((g_ours - g_ref).norm() / g_ref.norm()) < 1e-4
+
+
+def test_lr_step_first_selects_the_pti_schedule_order():
+    """cli_lora_pti.perform_tuning steps the scheduler BEFORE the update (iteration k runs at
+    lambda(k+1)); train_lora_dreambooth.py steps it after (lambda(k)). The golden of the real
+    perform_tuning loop recorded lrs 1e-4 * (1 - k/6) for k = 1, 2, 3."""
+    import os
+    from lora_b200.train import LoraTrainStep, StepConfig
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "pti_perform_tuning.pt"))
+
+    class Arena:
+        base_lr = [1e-4, 1e-5]
+
+        def set_lr(self, lrs):
+            self.seen.append(list(lrs))
+
+    for first, offset in ((True, 1), (False, 0)):
+        tr = object.__new__(LoraTrainStep)
+        tr.cfg = StepConfig(lr_scheduler="linear", lr_warmup_steps=0, max_train_steps=6, lr_step_first=first)
+        tr.arena, tr.global_step, tr.graph = Arena(), 0, None
+        tr.arena.seen = []
+        tr.loss = None
+        tr._body = lambda: None
+        for _ in range(3):
+            tr.step_device()
+        want = [[1e-4 * (1 - (k + offset) / 6), 1e-5 * (1 - (k + offset) / 6)] for k in range(3)]
+        assert all(abs(a - b) < 1e-18 for got, w in zip(tr.arena.seen, want) for a, b in zip(got, w))
+        if first:       # exactly what the reference loop used
+            assert all(abs(a - b) < 1e-12 for got, st in zip(tr.arena.seen, G["steps"]) for a, b in zip(got, st["lrs"]))
