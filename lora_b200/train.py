@@ -61,6 +61,11 @@ class StepConfig:
     # cat([noisy latents, mask, masked-image latents], dim=1); both extra inputs are per-sample
     # data at latent resolution, in `self.inpaint_mask` / `self.masked_latents`
     train_inpainting: bool = False
+    # Dreambooth prior preservation (train_lora_dreambooth.py:855-873): the batch is
+    # [instance images ; class images]; loss = mse(instance).mean([1,2,3]).mean()
+    # + prior_loss_weight * mse(class)
+    with_prior_preservation: bool = False
+    prior_loss_weight: float = 1.0
 
 
 class LoraTrainStep:
@@ -125,12 +130,20 @@ class LoraTrainStep:
                     ehs = self.text_encoder(self.input_ids)[0]
             noisy = noisy.to(self.model_dtype).contiguous(memory_format=torch.channels_last)
             pred = self.unet(noisy, timesteps, ehs.to(self.model_dtype)).sample
+        target = noise
         if cfg.use_mask:
             m = (self.mask.float() + 0.01).pow(cfg.mask_temperature)
             m = m / m.max()
-            loss = F.mse_loss((pred * m).float(), (noise * m).float(), reduction="none").mean([1, 2, 3]).mean()
+            pred, target = pred * m, target * m
+        if cfg.with_prior_preservation:
+            pred, pred_prior = torch.chunk(pred, 2, dim=0)
+            target, target_prior = torch.chunk(target, 2, dim=0)
+            loss = (F.mse_loss(pred.float(), target.float(), reduction="none").mean([1, 2, 3]).mean()
+                    + cfg.prior_loss_weight * F.mse_loss(pred_prior.float(), target_prior.float(), reduction="mean"))
+        elif cfg.use_mask:
+            loss = F.mse_loss(pred.float(), target.float(), reduction="none").mean([1, 2, 3]).mean()
         else:
-            loss = F.mse_loss(pred.float(), noise.float(), reduction="mean")
+            loss = F.mse_loss(pred.float(), target.float(), reduction="mean")
         from . import ops
         ops.set_side_stream(self._side)
         try:

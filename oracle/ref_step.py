@@ -48,10 +48,11 @@ class RefDreamboothStep:
         text_encoder.train()
 
     def forward_loss(self, latents, input_ids, noise, timesteps, loss_mask=None, mask_temperature=1.0,
-                     inpaint=None):
+                     inpaint=None, prior_loss_weight=None):
         """loss of cli_lora_pti.py:260-370 (`loss_step`, epsilon prediction, cached latents).
         loss_mask: [B,1,8h,8w] image-resolution mask (`batch["mask"]`, :340-368) or None;
-        inpaint: (mask [B,1,h,w], masked_image_latents [B,4,h,w]) for the 9-channel UNet (:279-313)."""
+        inpaint: (mask [B,1,h,w], masked_image_latents [B,4,h,w]) for the 9-channel UNet (:279-313);
+        prior_loss_weight: Dreambooth prior preservation (train_lora_dreambooth.py:855-873) or None."""
         noisy = self.noiser.add_noise(latents, noise, timesteps)
         model_in = noisy if inpaint is None else torch.cat([noisy, inpaint[0], inpaint[1]], dim=1)
         dev = latents.device.type
@@ -71,6 +72,13 @@ class RefDreamboothStep:
             m = (m + 0.01).pow(mask_temperature)
             m = m / m.max()
             pred, target = pred * m, target * m
+        if prior_loss_weight is not None:
+            # train_lora_dreambooth.py:855-873: batch = [instance ; class], two losses
+            pred, pred_prior = torch.chunk(pred, 2, dim=0)
+            target, target_prior = torch.chunk(target, 2, dim=0)
+            inst = F.mse_loss(pred.float(), target.float(), reduction="none").mean([1, 2, 3]).mean()
+            return inst + prior_loss_weight * F.mse_loss(pred_prior.float(), target_prior.float(), reduction="mean")
+        if loss_mask is not None:
             return F.mse_loss(pred.float(), target.float(), reduction="none").mean([1, 2, 3]).mean()
         return F.mse_loss(pred.float(), target.float(), reduction="mean")
 

@@ -291,8 +291,9 @@ def test_injected_model_survives_deepcopy_and_pickle(tmp_path):
     assert [type(m).__name__ for m in _sites(back)] == [type(m).__name__ for m in a]
 
 
-@pytest.mark.parametrize("inpaint,masked", [(False, False), (False, True), (True, False), (True, True)])
-def test_train_step_forward_backward_body_on_cpu_doubles(inpaint, masked):
+@pytest.mark.parametrize("inpaint,masked,prior", [(False, False, False), (False, True, False), (True, False, False),
+                                                  (True, True, False), (False, False, True)])
+def test_train_step_forward_backward_body_on_cpu_doubles(inpaint, masked, prior):
     """lora_b200.train.LoraTrainStep._fwd_bwd (noise draw, t_multiplier, inpainting concat, masked
     loss, set_loss_mask's resize) exercised WITHOUT a GPU: the object is assembled by hand around
     CPU host models whose LoRA sites are the oracle's eager modules (the product's own modules have
@@ -316,7 +317,7 @@ def test_train_step_forward_backward_body_on_cpu_doubles(inpaint, masked):
     shape = (2, 4, 8, 8)
     tr = object.__new__(LoraTrainStep)              # no arena / CUDA buffers: only what _fwd_bwd touches
     tr.cfg = StepConfig(use_cuda_graph=False, t_multiplier=0.8, use_mask=masked, mask_temperature=2.0,
-                        train_inpainting=inpaint)
+                        train_inpainting=inpaint, with_prior_preservation=prior, prior_loss_weight=0.7)
     tr.unet, tr.text_encoder, tr.device = unet, text, torch.device("cpu")
     tr.noiser, tr.model_dtype, tr._side = DDPMNoiser(device="cpu"), torch.float32, None
     tr.latents = torch.randn(shape, generator=g) * 0.18215
@@ -332,6 +333,8 @@ def test_train_step_forward_backward_body_on_cpu_doubles(inpaint, masked):
         tr.inpaint_mask = (torch.rand(2, 1, 8, 8, generator=g) > 0.5).float()
         tr.masked_latents = torch.randn(shape, generator=g) * 0.18215
         kw.update(inpaint=(tr.inpaint_mask, tr.masked_latents))
+    if prior:
+        kw.update(prior_loss_weight=0.7)
     ref = RefDreamboothStep(unet, text, DDPMNoiser(device="cpu"), us, ts, t_multiplier=0.8)
     torch.manual_seed(77)
     noise = torch.randn(shape)
