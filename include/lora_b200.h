@@ -67,8 +67,13 @@ int lb_lora_linear_fwd_grouped(int n, const void* const* X, const void* const* W
                                float* const* T_out, const int* M, const int* K, const int* N,
                                const int* r, int in_dtype, int out_dtype, void* stream);
 
-/* Benchmark/profiling knob: tile schedule of lb_lora_linear_fwd. 0 = auto (default),
- * 1 = one tile per CTA, 2 = persistent CTAs with double-buffered TMEM accumulators. */
+/* Benchmark/profiling knob: tile schedule of lb_lora_linear_fwd.
+ *   mode = schedule + 4 * block_n + 16 * split
+ *   schedule: 0 = auto (default), 1 = one tile per CTA, 2 = persistent CTAs with double-buffered
+ *             TMEM accumulators, 3 = EXPERIMENTAL cluster split-K (csrc/fused_splitk.cuh; never
+ *             chosen by `auto`)
+ *   block_n:  0 = auto, 1 = 64, 2 = 128
+ *   split:    (schedule 3 only) 0 = auto (4), 1..3 = 2..4 CTAs of one cluster share a tile's K loop */
 int lb_debug_set_linear_mode(int mode);
 /* Profiling knob: device buffer (16 x uint64) receiving %globaltimer phase stamps of CTA (0,0) of
  * subsequent lb_lora_linear_fwd launches; NULL switches it off. */
