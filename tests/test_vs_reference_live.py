@@ -144,3 +144,90 @@ def test_oracle_inject_order_equals_reference(R):
         assert tuple(a.down.shape) == tuple(b.lora_down.weight.shape)
         wb = b.linear.weight if hasattr(b, "linear") else b.conv.weight
         assert a.weight is not None and torch.equal(a.weight, wb)
+
+
+def test_small_helpers_equal_reference(R, tmp_path):
+    """The remaining small public functions, side by side with the reference on the tiny UNet:
+    _find_children, extract_lora_ups_down, save_lora_as_json, save_lora_weight (.pt),
+    load_safeloras / load_safeloras_embeds / load_safeloras_both, _ti_lora_path,
+    load_learned_embed_in_clip."""
+    import filecmp
+    torch.manual_seed(0)
+    base = UNet2DConditionModel(UNetConfig.tiny())
+    ours, ref = copy.deepcopy(base), copy.deepcopy(base)
+    # _find_children: same (parent, name, child) walk on an un-injected model
+    a = [(type(p).__name__, n, tuple(c.weight.shape)) for p, n, c in L._find_children(ours, [nn.Linear, nn.Conv2d])]
+    b = [(type(p).__name__, n, tuple(c.weight.shape)) for p, n, c in R._find_children(ref, [nn.Linear, nn.Conv2d])]
+    assert a == b and len(a) > 20
+    torch.manual_seed(1)
+    L.inject_trainable_lora(ours, r=4)
+    torch.manual_seed(1)
+    R.inject_trainable_lora(ref, r=4)
+    g = torch.Generator().manual_seed(2)
+    for so, sr in zip(_sites(ours), _sites(ref)):
+        assert torch.equal(so.lora_down.weight, sr.lora_down.weight)      # ctor RNG parity
+        so.lora_up.weight.data.normal_(0, 0.02, generator=g)
+        sr.lora_up.weight.data.copy_(so.lora_up.weight.data)
+    eo, er = L.extract_lora_ups_down(ours), R.extract_lora_ups_down(ref)
+    assert len(eo) == len(er) == len(_sites(ours))
+    assert all(torch.equal(x[0].weight, y[0].weight) and torch.equal(x[1].weight, y[1].weight) for x, y in zip(eo, er))
+    # json / .pt writers: identical bytes (json) and identical tensors (.pt)
+    L.save_lora_as_json(ours, str(tmp_path / "o.json"))
+    R.save_lora_as_json(ref, str(tmp_path / "r.json"))
+    assert filecmp.cmp(tmp_path / "o.json", tmp_path / "r.json", shallow=False)
+    L.save_lora_weight(ours, str(tmp_path / "o.pt"))
+    R.save_lora_weight(ref, str(tmp_path / "r.pt"))
+    wo, wr = torch.load(tmp_path / "o.pt"), torch.load(tmp_path / "r.pt")
+    assert len(wo) == len(wr) and all(torch.equal(x, y) for x, y in zip(wo, wr))
+    # safetensors loaders
+    emb = {"<tok>": torch.randn(48, generator=g)}
+    L.save_safeloras_with_embeds({"unet": (ours, L.UNET_DEFAULT_TARGET_REPLACE)}, emb, str(tmp_path / "x.safetensors"))
+    for fn in ("load_safeloras", "load_safeloras_embeds", "load_safeloras_both"):
+        go, gr = getattr(L, fn)(str(tmp_path / "x.safetensors")), getattr(R, fn)(str(tmp_path / "x.safetensors"))
+        flat = lambda d: {k: ([torch.as_tensor(t) for t in v[0]], v[1], sorted(v[2])) for k, v in d.items()} \
+            if all(isinstance(v, tuple) for v in d.values()) else d
+        if fn == "load_safeloras_both":
+            go, gr = (flat(go[0]), go[1]), (flat(gr[0]), gr[1])
+            assert go[1].keys() == gr[1].keys() and all(torch.equal(go[1][k], gr[1][k]) for k in gr[1])
+            go, gr = go[0], gr[0]
+        elif fn == "load_safeloras":
+            go, gr = flat(go), flat(gr)
+        else:
+            assert go.keys() == gr.keys() and all(torch.equal(go[k], gr[k]) for k in gr)
+            continue
+        assert go.keys() == gr.keys()
+        for k in gr:
+            assert go[k][1] == gr[k][1] and go[k][2] == gr[k][2]
+            assert all(torch.equal(x, y) for x, y in zip(go[k][0], gr[k][0]))
+    assert L._ti_lora_path("a/b.c.pt") == R._ti_lora_path("a/b.c.pt")
+    assert L._text_lora_path("a/b.c.pt") == R._text_lora_path("a/b.c.pt")
+    # learned-embedding loader on two identical tiny text encoders with a duck tokenizer
+    class Tok:
+        def __init__(self, n):
+            self.v = {f"w{i}": i for i in range(n)}
+
+        def add_tokens(self, t):
+            if t in self.v:
+                return 0
+            self.v[t] = len(self.v)
+            return 1
+
+        def convert_tokens_to_ids(self, t):
+            return self.v[t]
+
+        def __len__(self):
+            return len(self.v)
+    torch.manual_seed(3)
+    te_o = build_text_encoder(tiny=True)
+    te_r = copy.deepcopy(te_o)
+    V = te_o.get_input_embeddings().weight.shape[0]
+    torch.save(emb, tmp_path / "e.pt")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.manual_seed(4)
+        L.load_learned_embed_in_clip(str(tmp_path / "e.pt"), te_o, Tok(V), token=None, idempotent=True)
+        torch.manual_seed(4)
+        R.load_learned_embed_in_clip(str(tmp_path / "e.pt"), te_r, Tok(V), token=None, idempotent=True)
+    assert torch.equal(te_o.get_input_embeddings().weight, te_r.get_input_embeddings().weight)
+    assert torch.equal(te_o.get_input_embeddings().weight[V], emb["<tok>"])
