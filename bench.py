@@ -280,7 +280,8 @@ def run_native(args):
         if type(m).__name__ in ("LoraInjectedLinear", "LoraInjectedConv2d"):
             m.lora_up.weight.data.normal_(0.0, 0.01, generator=g)
 
-    cfg = StepConfig(compute_dtype=dt, use_cuda_graph=not args.no_graph)
+    cfg = StepConfig(compute_dtype=dt, use_cuda_graph=not args.no_graph,
+                     capture_collective=args.capture_collective)
     seq = 77
     trainer = LoraTrainStep(unet, text, cfg, latent_shape=(1, 4, L_lat, L_lat), seq_len=seq, device=dev)
     vocab = text.config.vocab_size
@@ -473,6 +474,8 @@ def main():
     ap.add_argument("--extended", action="store_true", help="configs[2]: extended (conv) LoRA sites")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-group", action="store_true", help="one launch per LoRA site (no grouped launches)")
+    ap.add_argument("--capture-collective", action="store_true",
+                    help="EXPERIMENTAL: all-reduce inside ONE step graph (thread-local capture mode); run under timeout")
     ap.add_argument("--profile-steps", type=int, default=0, help="run N eager steps and exit (for ncu)")
     ap.add_argument("--roofline-only", action="store_true", help="one eager sweep of the fused kernel (for ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -40,6 +40,12 @@ class StepConfig:
     # (they feed only the optimizer); joined before the all-reduce. Measured neutral on C2
     # (59.9 vs 60.2 images/s): off by default.
     async_wgrad: bool = False
+    # EXPERIMENTAL (not yet run on hardware): capture the NCCL all-reduce INSIDE one step graph,
+    # with capture_error_mode="thread_local" so that the NCCL watchdog thread's event queries do
+    # not collide with the capture (the suspected cause of the round-1 dead-lock with a globally
+    # scoped capture). Saves the host gap between the two replays (~1 ms/step measured at N=8).
+    # Try it at N=2 under `timeout` first.
+    capture_collective: bool = False
     # accelerate-style mixed precision (fp32 frozen weights + torch.autocast), the reference's
     # own configuration (train_lora_dreambooth.py:489-494). None: run in the models' own dtype.
     autocast_dtype: Optional[torch.dtype] = None
@@ -184,6 +190,14 @@ class LoraTrainStep:
                 self._body()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        if self.cfg.capture_collective and self._world > 1:
+            import torch.distributed as dist
+            dist.barrier()                      # every rank enters its capture at the same time
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._body()
+            self.graph, self.graph_update = g, None
+            return
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
             self._fwd_bwd()
@@ -223,8 +237,9 @@ class LoraTrainStep:
         self.global_step += 1
         if self.graph is not None:
             self.graph.replay()
-            self.arena.allreduce_grads()
-            self.graph_update.replay()
+            if self.graph_update is not None:   # two graphs around an eager collective (default)
+                self.arena.allreduce_grads()
+                self.graph_update.replay()
         else:
             self._body()
         return self.loss
