@@ -17,7 +17,7 @@ parity is stated on singular values, on the rank-r product before clamping and o
 """
 import ctypes
 from collections import defaultdict
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
@@ -113,11 +113,21 @@ def _iter_lora(model):
 
 
 def overwrite_base(base_model: nn.Module, tuned_model: nn.Module, rank: int, clamp_quantile: float,
-                   power_iters: int = 2):
+                   power_iters: int = 2, shard: Optional[Tuple[int, int]] = None):
     """cli_svd.py:24-92 on two LoRA-injected models with identical site structure: the factors of
-    `base_model`'s sites are overwritten with the rank-`rank` distillation of (tuned - base)."""
+    `base_model`'s sites are overwritten with the rank-`rank` distillation of (tuned - base).
+
+    shard=(rank, world) (SURVEY.md 8e, config C5 on several GPUs): the weight deltas are
+    independent, so this process distils only sites i = rank (mod world) in traversal order -- no
+    collective on the compute path -- and the factors are then exchanged with ONE SUM all-reduce
+    over a zero-initialised flat fp32 buffer in which every rank has filled only its own slots
+    (exact: each slot receives one value plus zeros). Every rank ends with all sites overwritten."""
+    sites = list(zip(_iter_lora(base_model), _iter_lora(tuned_model)))
+    me, world = shard if shard is not None else (0, 1)
     groups = defaultdict(list)
-    for sb, st_ in zip(_iter_lora(base_model), _iter_lora(tuned_model)):
+    for i, (sb, st_) in enumerate(sites):
+        if i % world != me:
+            continue
         hb = sb.linear if hasattr(sb, "linear") else sb.conv
         ht = st_.linear if hasattr(st_, "linear") else st_.conv
         wb, wt = hb.weight.data, ht.weight.data
@@ -137,10 +147,31 @@ def overwrite_base(base_model: nn.Module, tuned_model: nn.Module, rank: int, cla
             assert site.lora_down.weight.flatten(1).shape == d.shape
             site.lora_up.weight.data = u.reshape(site.lora_up.weight.shape).to(device=dev, dtype=dt)
             site.lora_down.weight.data = d.reshape(site.lora_down.weight.shape).to(device=dev, dtype=dt)
+    if world > 1:
+        _exchange_factors([sb for sb, _ in sites], me, world)
+
+
+def _exchange_factors(sites, me: int, world: int):
+    """Every rank holds valid factors for sites i = me (mod world); after this every rank holds all."""
+    from .dist import allreduce_sum_
+    tensors = [t for s in sites for t in (s.lora_up.weight, s.lora_down.weight)]
+    owners = [i % world for i in range(len(sites)) for _ in range(2)]
+    flat = torch.zeros(sum(t.numel() for t in tensors), dtype=torch.float32, device=tensors[0].device)
+    off = 0
+    for t, owner in zip(tensors, owners):
+        if owner == me:
+            flat[off:off + t.numel()] = t.data.flatten().float()
+        off += t.numel()
+    allreduce_sum_(flat)
+    off = 0
+    for t in tensors:
+        t.data = flat[off:off + t.numel()].reshape(t.shape).to(t.dtype)
+        off += t.numel()
 
 
 def svd_distill(unet_base: nn.Module, unet_tuned: nn.Module, text_base: nn.Module, text_tuned: nn.Module,
-                rank: int = 4, clamp_quantile: float = 0.99, save_path: str = "svd_distill.safetensors"):
+                rank: int = 4, clamp_quantile: float = 0.99, save_path: str = "svd_distill.safetensors",
+                shard: Optional[Tuple[int, int]] = None):
     """cli_svd.py:95-142 with module arguments instead of hub ids (diffusers pipelines cannot be
     loaded offline): inject (extended for the UNet, CLIPAttention for the text encoder), distill,
     save with save_all (which, like the reference, writes only the default-target UNet sites)."""
@@ -148,9 +179,11 @@ def svd_distill(unet_base: nn.Module, unet_tuned: nn.Module, text_base: nn.Modul
     from .persist import save_all
     inject_trainable_lora_extended(unet_base, r=rank)
     inject_trainable_lora_extended(unet_tuned, r=rank)
-    overwrite_base(unet_base, unet_tuned, rank=rank, clamp_quantile=clamp_quantile)
+    overwrite_base(unet_base, unet_tuned, rank=rank, clamp_quantile=clamp_quantile, shard=shard)
     inject_trainable_lora(text_base, r=rank, target_replace_module={"CLIPAttention"})
     inject_trainable_lora(text_tuned, r=rank, target_replace_module={"CLIPAttention"})
-    overwrite_base(text_base, text_tuned, rank=rank, clamp_quantile=clamp_quantile)
+    overwrite_base(text_base, text_tuned, rank=rank, clamp_quantile=clamp_quantile, shard=shard)
+    if shard is not None and shard[0] != 0:
+        return                              # sharded run: every rank holds all factors, rank 0 writes
     save_all(unet=unet_base, text_encoder=text_base, placeholder_token_ids=None, placeholder_tokens=None,
              save_path=save_path, save_lora=True, save_ti=False)

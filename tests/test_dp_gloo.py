@@ -67,3 +67,79 @@ def test_shard_indices_round_robin():
         for r in range(world):
             seen.update(shard_indices(10, r, world))
         assert seen == set(range(10))
+
+
+def _cpu_svd_stub(W_tuned, W_base, rank, power_iters=2):
+    """Exact truncated SVD on CPU standing in for the CUDA kernels (same return contract as
+    lora_b200.svd.svd_lowrank_batched): the test below is about WHICH process distils WHICH site and
+    how the factors travel, not about the factorisation."""
+    ups, downs, sig = [], [], []
+    for wt, wb in zip(W_tuned, W_base):
+        U, S, Vh = torch.linalg.svd(wt.float() - wb.float(), full_matrices=False)
+        ups.append(U[:, :rank] * S[:rank])
+        downs.append(Vh[:rank])
+        sig.append(S[:rank])
+    return torch.stack(ups), torch.stack(downs), torch.stack(sig)
+
+
+def _build_pair():
+    import copy
+    import lora_b200 as L
+    from lora_b200.host.unet_sd15 import UNet2DConditionModel, UNetConfig
+    torch.manual_seed(0)
+    base = UNet2DConditionModel(UNetConfig.tiny())
+    tuned = copy.deepcopy(base)
+    g = torch.Generator().manual_seed(1)
+    for prm in tuned.parameters():
+        if prm.dim() >= 2:
+            prm.data.add_(torch.randn(prm.shape, generator=g) * 0.01)
+    L.inject_trainable_lora_extended(base, r=4)
+    L.inject_trainable_lora_extended(tuned, r=4)
+    return base, tuned
+
+
+def _factors(model):
+    return [t.detach().clone() for m in model.modules() if type(m).__name__.startswith("LoraInjected")
+            for t in (m.lora_up.weight, m.lora_down.weight)]
+
+
+def _svd_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    import lora_b200.svd as svd
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seen = []
+    def stub(W_tuned, W_base, r, power_iters=2):
+        seen.append(len(W_tuned))
+        return _cpu_svd_stub(W_tuned, W_base, r, power_iters)
+    svd.svd_lowrank_batched = stub
+    base, tuned = _build_pair()
+    svd.overwrite_base(base, tuned, rank=4, clamp_quantile=0.99, shard=(rank, world))
+    torch.save({"factors": _factors(base), "n_done": sum(seen)}, os.path.join(out_dir, f"svd{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_svd_distill_equals_single_process(tmp_path):
+    """SURVEY.md 8(e), config C5 on several GPUs: weight deltas are sharded round-robin over the
+    ranks (no collective on the compute path), factors exchanged by one all-reduce over a
+    zero-padded flat buffer; every rank must end with exactly the single-process result."""
+    import lora_b200.svd as svd
+    world = 2
+    mp.spawn(_svd_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(tmp_path / f"svd{r}.pt") for r in range(world)]
+    real = svd.svd_lowrank_batched
+    try:
+        svd.svd_lowrank_batched = _cpu_svd_stub
+        base, tuned = _build_pair()
+        svd.overwrite_base(base, tuned, rank=4, clamp_quantile=0.99)
+    finally:
+        svd.svd_lowrank_batched = real
+    want = _factors(base)
+    n_sites = len(want) // 2
+    assert outs[0]["n_done"] + outs[1]["n_done"] == n_sites and abs(outs[0]["n_done"] - outs[1]["n_done"]) <= 1
+    for r in range(world):
+        got = outs[r]["factors"]
+        assert len(got) == len(want)
+        assert all(torch.equal(a, b) for a, b in zip(got, want)), r
