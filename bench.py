@@ -3,6 +3,7 @@
 
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
   python bench.py --impl reference ...                     (the reference's CPU path, oracle port)
+  python bench.py --impl reference-cuda ...                (the reference's path on the same GPU: torch eager)
 
 One "step" = one full Dreambooth LoRA training step at bs = 1 per GPU: text encoder (48 LoRA
 sites) -> UNet (144 LoRA sites) forward, MSE, backward (dX, dA, dB; W frozen), gradient
@@ -32,6 +33,21 @@ import torch  # noqa: E402
 METRIC = "sd15_lora_r4_512px_train_images_per_sec"
 UNIT = "images/s"
 WORKLOAD = "SD1.5 UNet+text_encoder LoRA rank=4 512x512 bf16 bs=1/GPU dreambooth step (configs[1])"
+
+
+def bench_config(args, world, lora_sites=None, lora_params=None):
+    """The `config` object of the JSON line -- identical keys and values for every arm of the same
+    invocation, so the driver can check that both arms ran the same workload."""
+    if args.tiny:
+        wl = "TINY smoke config (not a bench)"
+    elif args.extended:
+        wl = ("SD1.5 --use_extended_lora (ResBlock Conv2d LoRA, dropout 0.1) UNet+text_encoder 512x512 bf16 "
+              "bs=1/GPU (configs[2] shape)")
+    else:
+        wl = WORKLOAD
+    return {"workload": wl, "extended": bool(args.extended), "resolution": args.res, "rank": args.rank,
+            "global_batch": world, "parallelism": f"dp{world}",
+            "l2": "working set per step (>=1.7 GB frozen weights + activations) exceeds the 126 MB L2; no explicit flush"}
 
 
 def load_peaks():
@@ -248,12 +264,18 @@ def run_native(args):
     torch.backends.cudnn.benchmark = True   # host-model convs: let cuDNN pick its kernels in warm-up
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("LB_NCCL_DEBUG", "WARN")
-        # NCCL prints its version banner to STDOUT at communicator creation; stdout carries exactly
-        # one JSON line, so park fd 1 on stderr while the communicator is built
+        # An externally set NCCL_DEBUG (the driver's communicator check reads NCCL's INFO lines) is
+        # honoured and NCCL's output is left where NCCL puts it. Only when nobody asked for NCCL
+        # logging do we default to WARN and keep NCCL's version banner (printed to STDOUT at
+        # communicator creation) off stdout by parking fd 1 on stderr while the communicator is built.
+        external_nccl_debug = "NCCL_DEBUG" in os.environ
+        if not external_nccl_debug:
+            os.environ["NCCL_DEBUG"] = os.environ.get("LB_NCCL_DEBUG", "WARN")
         sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
+        saved = None
+        if not external_nccl_debug:
+            saved = os.dup(1)
+            os.dup2(2, 1)
         try:
             dist.init_process_group("nccl", device_id=dev)
             warm = torch.ones(1, device=dev)
@@ -261,8 +283,9 @@ def run_native(args):
             torch.cuda.synchronize()
         finally:
             sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+            if saved is not None:
+                os.dup2(saved, 1)
+                os.close(saved)
 
     dt = torch.bfloat16
     res = args.res
@@ -371,16 +394,10 @@ def run_native(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic latents/token ids, random-init SD1.5-shaped weights",
-            "config": {"workload": ("TINY smoke config (not a bench)" if args.tiny else
-                                    (WORKLOAD if not args.extended else
-                                     "SD1.5 --use_extended_lora (ResBlock Conv2d LoRA, dropout 0.1) UNet+text_encoder 512x512 bf16 bs=1/GPU (configs[2] shape)")),
-                       "extended": bool(args.extended),
-                       "resolution": res, "rank": args.rank, "global_batch": world,
-                       "lora_sites": len(shapes), "lora_params": trainer.arena.n_params,
-                       "parallelism": f"dp{world}", "cuda_graph": trainer.graph is not None, "grouped_launches": not args.no_group,
-                       "graph_error": trainer.graph_error,
-                       "l2": "working set per step (>=1.7 GB frozen weights + activations) exceeds the 126 MB L2; no explicit flush",
-                       "loss": loss_dev},
+            "config": bench_config(args, world),
+            "engine": {"lora_sites": len(shapes), "lora_params": trainer.arena.n_params,
+                       "cuda_graph": trainer.graph is not None, "grouped_launches": not args.no_group,
+                       "graph_error": trainer.graph_error, "loss": loss_dev},
             "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": trainer.h2d_bytes(), "d2h_bytes_per_step": trainer.d2h_bytes(),
                     "loss": loss_e2e},
@@ -395,6 +412,15 @@ def run_native(args):
                          "avg_launch_us": rms * 1e3 / n_l,
                          "share_of_step": rms / (ms_dev / args.steps), "peak_source": peak_src},
         }
+        if world == 1 and not args.no_cuda_baseline:
+            # the reference's operator modules (oracle port) in the same host models on THIS GPU:
+            # torch eager (what the reference runs) and, generously, the same step graph-replayed
+            del trainer
+            torch.cuda.empty_cache()
+            try:
+                out["cuda_eager_baseline"] = cuda_reference(dev, args, steps=args.steps, warmup=max(args.warmup, 3))
+            except Exception as e:   # a baseline must never take the native line down
+                out["cuda_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_reference(res, args.rank, budget_s=args.cpu_budget, tiny=args.tiny)
     if world > 1:
@@ -429,9 +455,12 @@ def cpu_reference(res, rank_r, budget_s=30.0, max_steps=None, warmup=1, tiny=Fal
     for _ in range(warmup):
         stepper.step(lat, ids)
     t_w = (time.perf_counter() - t_w) / max(warmup, 1)
-    n = max(1, int(budget_s / max(t_w, 1e-3)))
-    if max_steps is not None:
-        n = min(n, max_steps)
+    if budget_s is None:            # --impl reference: exactly the requested number of steps
+        n = max(1, int(max_steps))
+    else:                           # cpu_baseline block of the native line: a bounded sample
+        n = max(1, int(budget_s / max(t_w, 1e-3)))
+        if max_steps is not None:
+            n = min(n, max_steps)
     t0 = time.perf_counter()
     for _ in range(n):
         loss = stepper.step(lat, ids)
@@ -442,23 +471,134 @@ def cpu_reference(res, rank_r, budget_s=30.0, max_steps=None, warmup=1, tiny=Fal
             "ms_per_step": dt / n * 1e3, "steps": n, "loss": float(loss)}
 
 
+def cuda_reference(dev, args, steps, warmup):
+    """The reference's LoRA path on the SAME B200: its operator modules (oracle/ref_modules.py, the
+    three-GEMM + elementwise torch formulation of lora.py:53-58,130-135) injected into the same host
+    models, its step (oracle/ref_step.py: torch.optim.AdamW + clip_grad_norm_), torch eager -- the
+    stock way the reference runs on a GPU. Also timed as ONE CUDA-graph replay per step (something
+    the reference does not do) so that launch latency is taken out of the comparison. Two precision
+    set-ups: "bf16_model" = the native arm's host-model dtype (the reference casts its LoRA modules
+    to the weight dtype, lora.py:295); "autocast" = accelerate's mixed_precision=bf16
+    (fp32 weights + torch.autocast, train_lora_dreambooth.py:489-494)."""
+    from oracle.ref_modules import ref_inject
+    from oracle.ref_step import RefDreamboothStep
+    from lora_b200.host.ddpm import DDPMNoiser
+    L_lat = args.res // 8
+    out = {"unit": UNIT, "kind": "port", "steps": steps, "warmup": warmup,
+           "what": "oracle port of the reference step (RefLoraSite modules, torch.optim.AdamW, clip_grad_norm_) "
+                   f"on cuda, torch {torch.__version__}"}
+    for mode in (("bf16_model", "autocast") if not args.tiny else ("bf16_model",)):
+        mdt = torch.bfloat16 if mode == "bf16_model" else torch.float32
+        unet, text = build_models(dev, mdt, seed=0, tiny=args.tiny)
+        targets = {"CrossAttention", "Attention", "GEGLU"}
+        if args.extended:
+            us = ref_inject(unet, targets | {"ResnetBlock2D"}, r=args.rank, extended=True)
+        else:
+            us = ref_inject(unet, targets, r=args.rank)
+        ts = ref_inject(text, {"CLIPAttention"}, r=args.rank)
+        g = torch.Generator(device=dev).manual_seed(1)
+        for st in us + ts:
+            st.up.data.normal_(0.0, 0.01, generator=g)
+        stepper = RefDreamboothStep(unet, text, DDPMNoiser(device=dev), us, ts,
+                                    autocast_dtype=(torch.bfloat16 if mode == "autocast" else None), capturable=True)
+        torch.manual_seed(1234)
+        lat = torch.randn(1, 4, L_lat, L_lat, device=dev) * 0.18215
+        ids = torch.randint(0, text.config.vocab_size, (1, 77), device=dev)
+        loss_buf = torch.zeros((), device=dev)
+
+        def body():
+            loss_buf.copy_(stepper.step(lat, ids))
+
+        def timed(fn):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps
+
+        ms_eager = timed(body)
+        res = {"eager_ms_per_step": ms_eager, "eager_images_per_s": 1e3 / ms_eager, "loss": float(loss_buf)}
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                body()
+            ms_graph = timed(gr.replay)
+            res.update({"graphed_ms_per_step": ms_graph, "graphed_images_per_s": 1e3 / ms_graph})
+            del gr
+        except Exception as e:
+            res["graph_error"] = f"{type(e).__name__}: {e}"
+            torch.cuda.synchronize()
+        out[mode] = res
+        del stepper, unet, text, us, ts
+        torch.cuda.empty_cache()
+    best = out["bf16_model"]
+    out["value"] = best["eager_images_per_s"]
+    out["graphed_value"] = best.get("graphed_images_per_s")
+    return out
+
+
 def run_reference(args):
+    """--impl reference: the reference's own CPU path (oracle port; the reference package itself
+    cannot be imported: diffusers/accelerate/fire are absent) on the host cores, EXACTLY --steps
+    steps after --warmup warm-ups, rank 0 only. Imports nothing that maps liblora_b200.so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    cb = cpu_reference(args.res, args.rank, budget_s=args.cpu_budget * 6, max_steps=args.steps,
-                       warmup=min(max(args.warmup, 1), 2), tiny=args.tiny)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    warm = max(args.warmup, 1)
+    cb = cpu_reference(args.res, args.rank, budget_s=None, max_steps=args.steps, warmup=warm, tiny=args.tiny)
+    try:
+        from lora_b200 import _C
+        so_mapped = _C.is_loaded()
+    except Exception:
+        so_mapped = None
     return {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
-        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": cb["steps"], "warmup": min(max(args.warmup, 1), 2),
+        "n_gpus": world, "steps": cb["steps"], "warmup": warm,
         "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic latents/token ids, random-init SD1.5-shaped weights",
-        "config": {"workload": WORKLOAD, "resolution": args.res, "rank": args.rank,
-                   "note": "reference = pure-Python lora_diffusion on torch eager; it cannot be imported on this box "
-                           "(diffusers/accelerate/fire absent), so its step is the oracle port on the host cores"},
+        "config": bench_config(args, world),
+        "engine": {"note": "reference = pure-Python lora_diffusion on torch eager; it cannot be imported on this box "
+                           "(diffusers/accelerate/fire absent), so its step is the oracle port on the host cores",
+                   "native_library_mapped": so_mapped, "loss": cb["loss"]},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+    }
+
+
+def run_reference_cuda(args):
+    """--impl reference-cuda: the reference's path on the same GPU (see cuda_reference)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    if not torch.cuda.is_available():
+        return {"impl": "reference-cuda", "unavailable": "no CUDA device"}
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    torch.backends.cudnn.benchmark = True
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    cb = cuda_reference(dev, args, steps=args.steps, warmup=max(args.warmup, 3))
+    clocks = sampler.stop()
+    return {
+        "impl": "reference-cuda", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 / cb["value"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic latents/token ids, random-init SD1.5-shaped weights",
+        "config": bench_config(args, world), "cuda_eager_baseline": cb, "clocks": clocks, "gpu_launches": 0,
     }
 
 
@@ -467,7 +607,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "reference", "reference-cuda"])
     ap.add_argument("--res", type=int, default=512)
     ap.add_argument("--rank", type=int, default=4)
     ap.add_argument("--tiny", action="store_true", help="toy widths (smoke only, not a bench)")
@@ -479,9 +619,11 @@ def main():
     ap.add_argument("--profile-steps", type=int, default=0, help="run N eager steps and exit (for ncu)")
     ap.add_argument("--roofline-only", action="store_true", help="one eager sweep of the fused kernel (for ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cuda-baseline", action="store_true", help="skip the reference-on-this-GPU block")
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU-baseline work")
     args = ap.parse_args()
-    out = run_reference(args) if args.impl == "reference" else run_native(args)
+    out = (run_reference(args) if args.impl == "reference" else
+           run_reference_cuda(args) if args.impl == "reference-cuda" else run_native(args))
     if out is not None:
         print(json.dumps(out), flush=True)
 

@@ -78,6 +78,11 @@ int lb_debug_set_linear_mode(int mode);
 /* Profiling knob: device buffer (16 x uint64) receiving %globaltimer phase stamps of CTA (0,0) of
  * subsequent lb_lora_linear_fwd launches; NULL switches it off. */
 int lb_debug_set_stamp_buffer(void* dev_buf);
+/* Programmatic dependent launch for the fused kernels (cudaLaunchAttributeProgrammaticStream-
+ * Serialization): the prologue of a launch (barrier init, TMEM allocation, descriptor prefetch)
+ * overlaps the tail of the previous kernel in the stream. 0 = off, 1 = on; initial value from the
+ * environment variable LB_PDL. */
+int lb_debug_set_pdl(int on);
 
 /* Skinny weight-gradient reduction (streams S once, fp32 atomics into out):
  *     out[j*out_js + c*out_cs] += scale * diag[j] * sum_m V[m,j] * S[m,c]     j < r, c < C

@@ -1,7 +1,7 @@
 """ctypes binding of the C-ABI in include/lora_b200.h.
 
-The library is the product: there is no CPU or eager fallback behind these calls. Importing this
-module without a built liblora_b200.so raises, and every wrapper raises on a non-zero status.
+The library is the product: there is no CPU or eager fallback behind these calls. The first call
+without a built liblora_b200.so raises, and every wrapper raises on a non-zero status.
 """
 import ctypes
 import os
@@ -57,6 +57,7 @@ def _load():
         "lb_lora_merge": ([vp, i32, vp, vp, f32, vp, i32, i32, i32, vp], i32),
         "lb_split_bf16x3": ([vp, ll, vp, i32, i32, i32, vp], i32),
         "lb_debug_set_stamp_buffer": ([vp], i32),
+        "lb_debug_set_pdl": ([i32], i32),
         "lb_lora_wgrad_pair": ([vp, vp, vp, ll, ll, i32, vp, vp, vp, ll, ll, i32, vp, f32, i32, i32,
                                 f32, vp, i32, vp], i32),
         "lb_svd_mul": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, vp], i32),
@@ -83,7 +84,26 @@ def _load():
     return lib
 
 
-lib = _load()
+class _LazyLib:
+    """The library is mapped on first use (first kernel call, `build()`'s symbol check), not at
+    `import lora_b200`: the host-side file tools (persist, lora_add, join, to_ckpt,
+    pt_to_safetensors) and anything that only needs the host models import without a CUDA
+    toolchain or runtime, like the reference's package. There is still no fallback: the first
+    kernel call without a loadable library raises LoraB200Error."""
+    _lib = None
+
+    def __getattr__(self, name):
+        lib = _LazyLib._lib
+        if lib is None:
+            lib = _LazyLib._lib = _load()
+        return getattr(lib, name)
+
+
+lib = _LazyLib()
+
+
+def is_loaded() -> bool:
+    return _LazyLib._lib is not None
 EXPORTED = [n for n in ("lb_abi_version", "lb_lora_linear_fwd", "lb_lora_wgrad",
                         "lb_cast_rows_pad16", "lb_cast_weight", "lb_adamw_clip_step",
                         "lb_refresh_shadows", "lb_lora_wgrad_shift", "lb_lora_conv2d_fwd",

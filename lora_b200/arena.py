@@ -94,6 +94,12 @@ class LoraArena:
             w.requires_grad_(True)
             w.grad = self.g[o:o + n].view(w.shape)
 
+        # ---- data-parallel replicas start identical: what accelerate/DDP's wrap does for the
+        # reference (rank 0's parameters are broadcast, train_lora_dreambooth.py:744-757). Without
+        # it per-rank seeding, `loras=` resumes or a checkpoint patched on one rank would diverge
+        # silently, because only gradients are exchanged afterwards.
+        self.sync_replicas()
+
         # ---- 16-bit operand copies ("shadows") + the table the refresh kernel walks
         rows, sh_off, max_c = [], 0, 1
         self._shadow_slots = []  # (site, kind, off, C)
@@ -131,6 +137,19 @@ class LoraArena:
         self._publish_shadows()
         for s in (s for sg in site_groups for s in sg):
             s._lb.grad_sink = (self._gview(s, "down"), self._gview(s, "up"))
+
+    def sync_replicas(self, src: int = 0):
+        """Broadcast rank `src`'s LoRA factors and optimizer state (p, m, v, Adam's t) to every
+        rank; a no-op outside torch.distributed. Called at construction; call it again after
+        loading a checkpoint on one rank."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        for buf in (self.p, self.m, self.v, self.step_dev):
+            dist.broadcast(buf, src=src)
+        if hasattr(self, "shadow"):
+            self.refresh_shadows()
+            self._publish_shadows()
 
     # ------------------------------------------------------------------ helpers
     def _off_of(self, site, which):

@@ -27,7 +27,7 @@ def _geometry(conv):
 
 
 def _frozen_conv(st: _SiteState, weight, dtype, need_bwd: bool):
-    k = ("conv",) + _key(weight)
+    k = _key(weight, tag="conv")
     ent = st.w.get(dtype)
     if ent is not None and ent[0] != k:
         ent = None

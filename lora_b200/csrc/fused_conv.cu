@@ -14,12 +14,8 @@ static int launch_conv(const void* X, const void* W, const void* Dn, void* Y, co
                        int n_img, int down_cols, int out_dtype, cudaStream_t stream) {
   using S = Smem<BLOCK_N, STAGES, OutT, G>;
   auto kern = fused_lora_kernel<BLOCK_N, STAGES, OutT, true, G>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES) != cudaSuccess)
-      return LB_ERR_CUDA;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (!ensure_dyn_smem(reinterpret_cast<const void*>(kern), S::DYN_BYTES, attr_mask)) return LB_ERR_CUDA;
   const CUtensorMapDataType in_dt = p.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
   CUtensorMap tmX, tmW, tmD, tmY;
@@ -28,8 +24,8 @@ static int launch_conv(const void* X, const void* W, const void* Dn, void* Y, co
   if (!tmap_2d(&tmD, Dn, in_dt, 2, down_cols, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
   if (!tmap_nhwc(&tmY, Y, out_dt, sizeof(OutT), p.N, p.W, p.H, n_img, S::BOX_COLS, p.TW, p.TH)) return LB_ERR_TMAP;
   dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, n_img * p.tiles_h * p.tiles_w, 1);
-  kern<<<grid, NUM_THREADS, S::DYN_BYTES, stream>>>(tmX, tmW, tmD, tmY, p);
-  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+  return launch_ex(kern, grid, dim3(NUM_THREADS), S::DYN_BYTES, stream, 1, tmX, tmW, tmD, tmY, p) == cudaSuccess
+             ? LB_OK : LB_ERR_CUDA;
 }
 
 }  // namespace lb

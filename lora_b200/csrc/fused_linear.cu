@@ -15,12 +15,8 @@ static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, 
   using S = Smem<BLOCK_N, STAGES, OutT, 1>;
   auto kern = fused_lora_kernel<BLOCK_N, STAGES, OutT, false, 1, MIN_CTAS>;
   static_assert(MIN_CTAS * (S::DYN_BYTES + 1024) <= 233472 && MIN_CTAS * S::TMEM_COLS <= 512, "occupancy target does not fit");
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES) != cudaSuccess)
-      return LB_ERR_CUDA;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (!ensure_dyn_smem(reinterpret_cast<const void*>(kern), S::DYN_BYTES, attr_mask)) return LB_ERR_CUDA;
   const CUtensorMapDataType in_dt = p.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
   CUtensorMap tmX, tmW, tmD, tmY;
@@ -29,8 +25,8 @@ static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, 
   if (!tmap_2d(&tmD, Dn, in_dt, 2, p.K, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmY, Y, out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
   dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M, 1);
-  kern<<<grid, NUM_THREADS, S::DYN_BYTES, stream>>>(tmX, tmW, tmD, tmY, p);
-  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+  return launch_ex(kern, dim3(grid), dim3(NUM_THREADS), S::DYN_BYTES, stream, 1, tmX, tmW, tmD, tmY, p) == cudaSuccess
+             ? LB_OK : LB_ERR_CUDA;
 }
 
 template <int BLOCK_N, int STAGES, typename OutT>
@@ -38,17 +34,10 @@ static int launch_persistent(const void* X, const void* W, const void* Dn, void*
                              const FusedParams& p, int out_dtype, cudaStream_t stream) {
   using S = PSmem<BLOCK_N, STAGES, OutT>;
   auto kern = fused_lora_persistent_kernel<BLOCK_N, STAGES, OutT>;
-  static bool attr_set = false;
-  static int num_sms = 0;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES) != cudaSuccess)
-      return LB_ERR_CUDA;
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
-      return LB_ERR_CUDA;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (!ensure_dyn_smem(reinterpret_cast<const void*>(kern), S::DYN_BYTES, attr_mask)) return LB_ERR_CUDA;
+  const int num_sms = sm_count();
+  if (num_sms <= 0) return LB_ERR_CUDA;
   const CUtensorMapDataType in_dt = p.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
   CUtensorMap tmX, tmW, tmD, tmY;
@@ -58,8 +47,8 @@ static int launch_persistent(const void* X, const void* W, const void* Dn, void*
   if (!tmap_2d(&tmY, Y, out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
   const long long total = static_cast<long long>((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + BLOCK_M - 1) / BLOCK_M);
   const int grid = static_cast<int>(total < num_sms ? total : num_sms);
-  kern<<<grid, NUM_THREADS, S::DYN_BYTES, stream>>>(tmX, tmW, tmD, tmY, p);
-  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+  return launch_ex(kern, dim3(grid), dim3(NUM_THREADS), S::DYN_BYTES, stream, 1, tmX, tmW, tmD, tmY, p) == cudaSuccess
+             ? LB_OK : LB_ERR_CUDA;
 }
 
 template <int BLOCK_N, int STAGES, typename OutT, int MIN_CTAS>
@@ -67,12 +56,8 @@ static int launch_grouped(GroupedArgs& a, const void* const* X, const void* cons
                           const void* const* Dn, void* const* Y, int out_dtype, cudaStream_t stream) {
   using S = Smem<BLOCK_N, STAGES, OutT, 1>;
   auto kern = fused_lora_grouped_kernel<BLOCK_N, STAGES, OutT, MIN_CTAS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES) != cudaSuccess)
-      return LB_ERR_CUDA;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (!ensure_dyn_smem(reinterpret_cast<const void*>(kern), S::DYN_BYTES, attr_mask)) return LB_ERR_CUDA;
   const int fmt = a.p[0].fmt;
   const CUtensorMapDataType in_dt = fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
@@ -88,8 +73,7 @@ static int launch_grouped(GroupedArgs& a, const void* const* X, const void* cons
     total += a.n_tiles_n[i] * ((p.M + BLOCK_M - 1) / BLOCK_M);
   }
   for (int i = a.n_problems; i <= MAX_GROUP; ++i) a.tile_start[i] = total;
-  kern<<<total, NUM_THREADS, S::DYN_BYTES, stream>>>(a);
-  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+  return launch_ex(kern, dim3(total), dim3(NUM_THREADS), S::DYN_BYTES, stream, 1, a) == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }
 
 
@@ -99,12 +83,8 @@ static int launch_splitk(const void* X, const void* W, const void* Dn, void* Y, 
                          int out_dtype, cudaStream_t stream) {
   using S = SplitSmem<BLOCK_N, STAGES, OutT, SPLIT>;
   auto kern = fused_lora_splitk_kernel<BLOCK_N, STAGES, OutT, SPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES) != cudaSuccess)
-      return LB_ERR_CUDA;
-    attr_set = true;
-  }
+  static unsigned long long attr_mask = 0;
+  if (!ensure_dyn_smem(reinterpret_cast<const void*>(kern), S::DYN_BYTES, attr_mask)) return LB_ERR_CUDA;
   const CUtensorMapDataType in_dt = p.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
   CUtensorMap tmX, tmW, tmD, tmY;
@@ -112,19 +92,9 @@ static int launch_splitk(const void* X, const void* W, const void* Dn, void* Y, 
   if (!tmap_2d(&tmW, W, in_dt, 2, p.K, p.N, BLOCK_K, BLOCK_N, true)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmD, Dn, in_dt, 2, p.K, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmY, Y, out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M, SPLIT);
-  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = S::DYN_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = SPLIT;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, tmX, tmW, tmD, tmY, p) == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+  const dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M, SPLIT);
+  return launch_ex(kern, grid, dim3(NUM_THREADS), S::DYN_BYTES, stream, SPLIT, tmX, tmW, tmD, tmY, p) == cudaSuccess
+             ? LB_OK : LB_ERR_CUDA;
 }
 
 static int g_linear_mode = 0;
@@ -138,6 +108,12 @@ extern "C" int lb_debug_set_linear_mode(int mode) {
   // + 4 * block_n choice (0 auto, 1: 64, 2: 128) + 16 * split-K factor choice (0: auto, 1..3: 2..4 CTAs)
   if (mode < 0 || mode > 63 || ((mode >> 2) & 3) == 3) return LB_ERR_SHAPE;
   lb::g_linear_mode = mode;
+  return LB_OK;
+}
+
+// Programmatic dependent launch for the fused kernels (0 off, 1 on; default from env LB_PDL).
+extern "C" int lb_debug_set_pdl(int on) {
+  lb::pdl_flag() = on ? 1 : 0;
   return LB_OK;
 }
 

@@ -85,6 +85,7 @@ fused_lora_persistent_kernel(const __grid_constant__ CUtensorMap tmX,
     fence_mbar_init();
   }
   __syncthreads();  // barriers initialised
+  pdl_launch_dependents();   // the next kernel in the stream may start its own prologue now
   // The TMA producer starts streaming right away; TMEM allocation (a few hundred cycles) proceeds
   // concurrently in warp 1 and is published to the MMA/epilogue warps through named barrier 2.
   uint32_t tmem = 0;
@@ -98,6 +99,7 @@ fused_lora_persistent_kernel(const __grid_constant__ CUtensorMap tmX,
     tc_fence_after();
     tmem = *tmem_slot;
   }
+  pdl_wait();                // predecessor grid complete, its writes visible: global reads may start
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer

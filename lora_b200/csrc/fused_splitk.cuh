@@ -135,6 +135,7 @@ fused_lora_splitk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
   // cluster-wide: every CTA's barriers exist before any peer signals them
   cluster_arrive_relaxed();
   cluster_wait_acquire();
+  pdl_launch_dependents();
 
   uint32_t tmem = 0;
   if (warp != 0) {
@@ -147,6 +148,7 @@ fused_lora_splitk_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_c
     tc_fence_after();
     tmem = *tmem_slot;
   }
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (this CTA's K range)

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace lb {
 
@@ -11,6 +12,65 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cudaFuncSetAttribute is per DEVICE: remember which devices of this process already have the
+// dynamic shared memory limit of `func` raised (one bit per device ordinal; a process that drives
+// cuda:1 after cuda:0 -- single-process DP, tests on a second GPU -- must set it again).
+inline bool ensure_dyn_smem(const void* func, int bytes, unsigned long long& done_mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (dev >= 0 && dev < 64 && ((done_mask >> dev) & 1ull)) return true;
+  if (cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess)
+    return false;
+  if (dev >= 0 && dev < 64) done_mask |= 1ull << dev;
+  return true;
+}
+inline int sm_count() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  static int cached[64] = {0};
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 0;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
+  return n;
+}
+
+// Launch through cudaLaunchKernelEx so that launch attributes can be attached: a thread-block
+// cluster along z (cluster_z > 1) and/or programmatic dependent launch (pdl; see ptx.cuh).
+inline int& pdl_flag() {
+  static int flag = -1;
+  if (flag < 0) {
+    const char* e = getenv("LB_PDL");
+    flag = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return flag;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                             cudaStream_t stream, int cluster_z, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_z > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = 1;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = cluster_z;
+    ++n;
+  }
+  if (pdl_flag()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 inline EncodeTiledFn encode_tiled_fn() {
   static EncodeTiledFn fn = nullptr;

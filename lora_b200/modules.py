@@ -18,6 +18,7 @@ made by the reference's own inject/patch code keeps working; they are containers
 There is no eager fallback: a CPU tensor or a missing library raises LoraB200Error.
 """
 import math
+import weakref
 from typing import Optional
 
 import torch
@@ -65,8 +66,48 @@ def _out_dtype(x: torch.Tensor, cdt: torch.dtype) -> torch.dtype:
     return torch.float32
 
 
-def _key(t: Optional[torch.Tensor]):
-    return None if t is None else (id(t), t._version, t.data_ptr(), t.dtype, t.device)
+class _Key:
+    """Identity of a cached operand's source tensor: the tensor OBJECT (held weakly -- `id()` values
+    are recycled after garbage collection, a weak reference is not), its version counter, storage
+    address, dtype and device. Two keys are equal only while the original object is alive."""
+    __slots__ = ("ref", "ver", "ptr", "dtype", "device", "tag")
+
+    def __init__(self, t: torch.Tensor, tag=None):
+        self.ref = weakref.ref(t)
+        self.ver, self.ptr, self.dtype, self.device, self.tag = t._version, t.data_ptr(), t.dtype, t.device, tag
+
+    def __eq__(self, o):
+        if not isinstance(o, _Key):
+            return False
+        a = self.ref()
+        return (a is not None and a is o.ref() and self.ver == o.ver and self.ptr == o.ptr
+                and self.dtype == o.dtype and self.device == o.device and self.tag == o.tag)
+
+    def __ne__(self, o):
+        return not self.__eq__(o)
+
+    __hash__ = None
+
+
+def _key(t: Optional[torch.Tensor], tag=None):
+    return None if t is None else _Key(t, tag)
+
+
+def invalidate_caches(model: nn.Module):
+    """Drop every cached 16-bit operand of the LoRA sites under `model`. The caches follow
+    re-assignment (`.weight = ...`, `.weight.data = ...`) and version-counted in-place edits on
+    their own; an in-place edit made THROUGH `.data` (`p.data.copy_()`, `p.data.mul_()`, an EMA or
+    a hand-written weight loader) bumps no counter and moves no pointer -- call this afterwards.
+    Sites owned by a LoraArena re-publish their factor shadows at the next `arena.step()`."""
+    for m in model.modules():
+        st = m.__dict__.get("_lb")
+        if isinstance(st, _SiteState):
+            st.w.clear()
+            st.down.clear()
+            st.upT.clear()
+            st.bias = None
+            if hasattr(st, "w3"):      # precise_path.py's split-bf16 copies
+                st.w3 = None
 
 
 class _SiteState:

@@ -49,7 +49,8 @@ class StepConfig:
     # accelerate-style mixed precision (fp32 frozen weights + torch.autocast), the reference's
     # own configuration (train_lora_dreambooth.py:489-494). None: run in the models' own dtype.
     autocast_dtype: Optional[torch.dtype] = None
-    # lr_scheduler: "constant" (train_lora_dreambooth.py default) or "linear" decay to 0 over
+    # lr_scheduler: "constant" (train_lora_dreambooth.py default; ignores lr_warmup_steps like
+    # diffusers' get_scheduler), "constant_with_warmup", or "linear" decay to 0 over
     # max_train_steps after lr_warmup_steps (cli_lora_pti.py:730-741 `lr_scheduler_lora="linear"`)
     lr_scheduler: str = "constant"
     lr_warmup_steps: int = 0
@@ -72,6 +73,10 @@ class StepConfig:
     # + prior_loss_weight * mse(class)
     with_prior_preservation: bool = False
     prior_loss_weight: float = 1.0
+    # take the step's noise / timesteps from `self.noise` / `self.timesteps` (caller-filled static
+    # buffers) instead of drawing them inside the step: lets a parity test or a replayed trace feed
+    # the SAME draws to this engine and to the reference step, eager or graph-replayed
+    external_noise: bool = False
 
 
 class LoraTrainStep:
@@ -94,6 +99,9 @@ class LoraTrainStep:
         self.latents = torch.zeros(latent_shape, device=self.device, dtype=torch.float32)
         self.input_ids = torch.zeros((latent_shape[0], seq_len), device=self.device, dtype=torch.long)
         self.loss = torch.zeros((), device=self.device, dtype=torch.float32)
+        if cfg.external_noise:
+            self.noise = torch.zeros(latent_shape, device=self.device, dtype=torch.float32)
+            self.timesteps = torch.zeros((latent_shape[0],), device=self.device, dtype=torch.long)
         self.mask = torch.ones((latent_shape[0], 1, latent_shape[2], latent_shape[3]), device=self.device)
         if cfg.train_inpainting:
             self.inpaint_mask = torch.zeros((latent_shape[0], 1, latent_shape[2], latent_shape[3]), device=self.device)
@@ -120,9 +128,12 @@ class LoraTrainStep:
         cfg = self.cfg
         lat = self.latents
         bsz = lat.shape[0]
-        noise = torch.randn_like(lat)
-        t_max = int(self.noiser.num_train_timesteps * cfg.t_multiplier)
-        timesteps = torch.randint(0, t_max, (bsz,), device=lat.device).long()
+        if cfg.external_noise:
+            noise, timesteps = self.noise, self.timesteps
+        else:
+            noise = torch.randn_like(lat)
+            t_max = int(self.noiser.num_train_timesteps * cfg.t_multiplier)
+            timesteps = torch.randint(0, t_max, (bsz,), device=lat.device).long()
         noisy = self.noiser.add_noise(lat, noise, timesteps)
         if cfg.train_inpainting:
             noisy = torch.cat([noisy, self.inpaint_mask.to(noisy.dtype), self.masked_latents.to(noisy.dtype)], dim=1)
@@ -183,13 +194,41 @@ class LoraTrainStep:
         """Two graphs around the collective: [forward+backward] - NCCL all-reduce - [clip+AdamW].
         The all-reduce stays an ordinary stream-ordered NCCL call between the two replays (a
         collective inside a captured graph would tie every rank's capture to its peers')."""
+        # Warm-up runs real step bodies (cuDNN/cuBLAS autotuning, allocator pools, grouping
+        # families) but must not TRAIN: the arena (p, m, v, Adam's t), the loss buffer and the CUDA
+        # RNG stream are snapshotted here and restored after capture, so the first replay starts
+        # from exactly the state prepare() was called in and optimizer t stays in step with the
+        # lr schedule. (The reference has no warm-up; round 1 let these steps count.)
+        snap = self._snapshot()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(self.cfg.graph_warmup):
-                self._body()
-        torch.cuda.current_stream().wait_stream(side)
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(self.cfg.graph_warmup):
+                    self._body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._capture_graphs()
+        finally:
+            torch.cuda.synchronize()
+            self._restore(snap)
+
+    def _snapshot(self):
+        a = self.arena
+        return {"p": a.p.clone(), "m": a.m.clone(), "v": a.v.clone(), "step": a.step_dev.clone(),
+                "loss": self.loss.clone(), "rng": torch.cuda.get_rng_state(self.device)}
+
+    def _restore(self, snap):
+        a = self.arena
+        a.p.copy_(snap["p"]); a.m.copy_(snap["m"]); a.v.copy_(snap["v"]); a.step_dev.copy_(snap["step"])
+        a.g.zero_()
+        self.loss.copy_(snap["loss"])
+        a.refresh_shadows()
+        a._publish_shadows()
+        torch.cuda.set_rng_state(snap["rng"], self.device)
         torch.cuda.synchronize()
+
+    def _capture_graphs(self):
         if self.cfg.capture_collective and self._world > 1:
             import torch.distributed as dist
             dist.barrier()                      # every rank enters its capture at the same time
@@ -208,7 +247,8 @@ class LoraTrainStep:
 
     # ------------------------------------------------------------------ public API
     def prepare(self):
-        """Warm up and (optionally) capture. Counts graph_warmup optimizer steps."""
+        """Warm up and (optionally) capture. Leaves parameters, optimizer state and the RNG stream
+        exactly as it found them (the warm-up steps are rolled back)."""
         if self.cfg.use_cuda_graph and self.graph is None and self.graph_error is None:
             try:
                 self._capture()
@@ -219,8 +259,15 @@ class LoraTrainStep:
                 self.arena.zero_grad()
 
     def lr_multiplier(self, step: int) -> float:
-        """diffusers `get_scheduler` semantics for the two schedules the reference uses."""
+        """diffusers `get_scheduler` semantics: "constant" IGNORES num_warmup_steps (so the
+        reference's defaults, constant + 500 warm-up steps at train_lora_dreambooth.py:345-356, mean
+        no warm-up at all); "constant_with_warmup" and "linear" ramp 0 -> 1 over lr_warmup_steps,
+        "linear" then decays to 0 at max_train_steps."""
         cfg = self.cfg
+        if cfg.lr_scheduler == "constant":
+            return 1.0
+        if cfg.lr_scheduler not in ("linear", "constant_with_warmup"):
+            raise ValueError(f"lr_scheduler {cfg.lr_scheduler!r}: constant | constant_with_warmup | linear")
         if cfg.lr_warmup_steps > 0 and step < cfg.lr_warmup_steps:
             return float(step) / float(max(1, cfg.lr_warmup_steps))
         if cfg.lr_scheduler == "linear":
@@ -230,7 +277,7 @@ class LoraTrainStep:
 
     def step_device(self) -> torch.Tensor:
         """One step on inputs already resident in self.latents / self.input_ids."""
-        if self.cfg.lr_scheduler != "constant" or self.cfg.lr_warmup_steps > 0:
+        if self.cfg.lr_scheduler != "constant":
             k = self.global_step + (1 if self.cfg.lr_step_first else 0)
             mult = self.lr_multiplier(k)                     # host-side schedule, tiny async H2D copy
             self.arena.set_lr([b * mult for b in self.arena.base_lr])

@@ -147,7 +147,8 @@ def collapse_delta(A, B, alpha: float = 1.0):
     return alpha * (B.flatten(1) @ A.flatten(1))
 
 
-def lora_conv2d_backward(gy, x, W, A, B, scale: float, stride=1, padding=0, dilation=1, diag=None):
+def lora_conv2d_backward(gy, x, W, A, B, scale: float, stride=1, padding=0, dilation=1, diag=None,
+                         keep_mask=None, dropout_p: float = 0.0):
     """Autograd of lora.py:130-135 with the base conv frozen: returns (dX, dA, dB), written with
     the explicit transposed-convolution / weight-gradient operators (float64, no autograd graph).
 
@@ -162,6 +163,8 @@ def lora_conv2d_backward(gy, x, W, A, B, scale: float, stride=1, padding=0, dila
     t = _conv2d_naive(x, A, stride, padding, dilation)
     t_sel = torch.einsum("nchw,dc->ndhw", t, S)
     gu = gy * scale
+    if keep_mask is not None:                 # nn.Dropout on the branch (lora.py:115,133): same mask
+        gu = gu * _f(keep_mask) / (1.0 - dropout_p)
     B2 = B.reshape(B.shape[0], r)
     dB = torch.einsum("nohw,njhw->oj", gu, t_sel).reshape(B.shape)
     dT = torch.einsum("nohw,oj->njhw", gu, B2)

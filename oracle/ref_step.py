@@ -24,7 +24,7 @@ import torch.nn.functional as F
 class RefDreamboothStep:
     def __init__(self, unet, text_encoder, noiser, unet_sites: List, text_sites: Optional[List],
                  lr=1e-4, lr_text=5e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8,
-                 max_grad_norm=1.0, t_multiplier: float = 1.0, autocast_dtype=None):
+                 max_grad_norm=1.0, t_multiplier: float = 1.0, autocast_dtype=None, capturable: bool = False):
         self.unet, self.text_encoder, self.noiser = unet, text_encoder, noiser
         self.max_grad_norm = max_grad_norm
         self.t_multiplier = t_multiplier
@@ -43,7 +43,10 @@ class RefDreamboothStep:
         groups = [{"params": self.unet_params, "lr": lr}]
         if self.text_params:
             groups.append({"params": self.text_params, "lr": lr_text})
-        self.opt = torch.optim.AdamW(groups, lr=lr, betas=betas, weight_decay=weight_decay, eps=eps)
+        # capturable=True only so that bench.py can ALSO time this step as a CUDA-graph replay (the
+        # reference itself runs eager; the graphed figure is the generous comparator)
+        self.opt = torch.optim.AdamW(groups, lr=lr, betas=betas, weight_decay=weight_decay, eps=eps,
+                                     **({"capturable": True} if capturable else {}))
         unet.train()
         text_encoder.train()
 

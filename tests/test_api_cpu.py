@@ -267,6 +267,16 @@ def test_lr_schedule_restates_diffusers_linear_and_constant():
     assert abs(d.lr_multiplier(60) - 0.5) < 1e-12 and d.lr_multiplier(110) == 0.0 and d.lr_multiplier(500) == 0.0
     d.cfg = StepConfig(lr_scheduler="constant")
     assert d.lr_multiplier(0) == 1.0 and d.lr_multiplier(10 ** 6) == 1.0
+    # diffusers' "constant" ignores num_warmup_steps: the reference's defaults (constant, 500 warm-up
+    # steps; train_lora_dreambooth.py:345-356) mean NO warm-up
+    d.cfg = StepConfig(lr_scheduler="constant", lr_warmup_steps=500)
+    assert d.lr_multiplier(0) == 1.0 and d.lr_multiplier(3) == 1.0
+    d.cfg = StepConfig(lr_scheduler="constant_with_warmup", lr_warmup_steps=4)
+    assert [d.lr_multiplier(k) for k in (0, 1, 2, 4, 9)] == [0.0, 0.25, 0.5, 1.0, 1.0]
+    d.cfg = StepConfig(lr_scheduler="cosine")
+    import pytest
+    with pytest.raises(ValueError):
+        d.lr_multiplier(1)
 
 
 def test_injected_model_survives_deepcopy_and_pickle(tmp_path):

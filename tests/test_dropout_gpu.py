@@ -115,3 +115,37 @@ def test_conv_dropout_statistics_and_grads_finite():
     assert abs(keep_rate - 0.9) < 0.02, keep_rate
     for g in (x.grad, m.lora_down.weight.grad, m.lora_up.weight.grad):
         assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0
+
+
+def test_conv_dropout_backward_matches_oracle_with_recovered_mask():
+    """Conv site with active dropout: recover the realised keep-mask from the forward output
+    (branch / clean-branch ratio, as for the linear site above), then dX, dA, dB must equal the
+    oracle's backward (oracle/lora_ops.py::lora_conv2d_backward, autograd of lora.py:130-135)
+    evaluated WITH THAT MASK. The up factor is given a floor away from zero so that almost every
+    branch element is classifiable; the tolerance absorbs the few that are not."""
+    import lora_b200 as L
+    torch.manual_seed(2)
+    p, r, cin, cout, H = 0.2, 8, 64, 128, 16
+    m = L.LoraInjectedConv2d(cin, cout, 3, 1, 1, r=r, dropout_p=p, scale=1.25).to(DEV)
+    m.conv.requires_grad_(False)
+    m.lora_up.weight.data.normal_(0, 0.3)
+    x = (torch.randn(2, cin, H, H, device=DEV).to(torch.bfloat16)
+         .contiguous(memory_format=torch.channels_last).requires_grad_(True))
+    m.train()
+    y = m(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    W16 = m.conv.weight.detach().to(torch.bfloat16)
+    A, B = m.lora_down.weight.detach(), m.lora_up.weight.detach()
+    base = O.lora_conv2d_forward(x.detach(), W16, m.conv.bias, A, torch.zeros_like(B), 0.0, padding=1)
+    clean = O.lora_conv2d_forward(x.detach(), W16, m.conv.bias, A, B, 1.25, padding=1) - base
+    branch = y.detach().double().cpu() - base
+    ratio = branch / clean
+    kept = ratio.abs() > 0.5
+    big = clean.abs() > 0.05 * clean.abs().mean()
+    assert abs(float(kept[big].double().mean()) - (1 - p)) < 0.02
+    dX, dA, dB = O.lora_conv2d_backward(gy, x.detach(), W16, A, B, 1.25, padding=1,
+                                        keep_mask=kept.double(), dropout_p=p)
+    assert rel(x.grad, dX) < 3e-2
+    assert rel(m.lora_down.weight.grad, dA) < 3e-2
+    assert rel(m.lora_up.weight.grad, dB) < 3e-2
