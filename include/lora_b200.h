@@ -56,6 +56,20 @@ int lb_lora_linear_fwd(const void* X, const void* W, const float* bias, const vo
                        float scale, void* Y, float* T_out, const float* T_in, int M, int K, int N,
                        int r, int in_dtype, int out_dtype, void* stream);
 
+/* lb_lora_linear_fwd with an ACTIVE nn.Dropout(p) on the LoRA branch (lora.py:45,56: module in
+ * training mode, p > 0 -- the state of every site built by inject_trainable_lora_extended and the
+ * monkeypatch_* loaders), still ONE launch:
+ *     Y = X . W^T (+ bias) + keep(m,n)/(1-p) * (((X . down16^T) * (scale * diag)) . up^T)[m,n]
+ * The LoRA product keeps its own TMEM columns and the keep-mask (csrc/dropmask.cuh: a counter hash
+ * of (*seed_dev, m*N + n); seed_dev points to one uint64 in DEVICE memory so that a captured graph
+ * draws a new mask per replay) is applied while the tile is drained. Backward recomputes the same
+ * mask: lb_lora_dropout_dt, lb_lora_wgrad_masked / lb_lora_wgrad_pair(drop_p). */
+int lb_lora_linear_fwd_dropout(const void* X, const void* W, const float* bias, const void* down16,
+                               const float* up, long long up_rs, long long up_cs, const float* diag,
+                               float scale, void* Y, float* T_out, int M, int K, int N, int r,
+                               int in_dtype, int out_dtype, float drop_p, const void* seed_dev,
+                               void* stream);
+
 /* Up to 4 independent lb_lora_linear_fwd problems of the same operand/output dtype in ONE launch
  * (sites that share an input -- q/k/v of a self-attention, k/v of a cross-attention, CLIP's k/v/q --
  * each under-fill 148 SMs on their own). All array arguments are HOST arrays of length n; per-problem
@@ -166,6 +180,16 @@ int lb_lora_conv2d_fwd(const void* X, const void* W, const float* bias, const vo
                        int n_img, int H, int Wd, int Cin, int Cout, int kh, int kw, int pad_h,
                        int pad_w, int r, int per_tap_T, int in_dtype, int out_dtype, void* stream);
 
+/* lb_lora_conv2d_fwd (forward direction) with an active nn.Dropout(p) on the LoRA branch
+ * (lora.py:115,133; every conv site of inject_trainable_lora_extended): one launch, mask applied in
+ * the drain exactly as in lb_lora_linear_fwd_dropout; mask index = pixel * Cout + n with
+ * pixel = (img*H + h)*W + w. */
+int lb_lora_conv2d_fwd_dropout(const void* X, const void* W, const float* bias, const void* down16,
+                               const float* up, long long up_rs, long long up_cs, const float* diag,
+                               float scale, void* Y, float* T_out, int n_img, int H, int Wd, int Cin,
+                               int Cout, int kh, int kw, int pad_h, int pad_w, int r, int in_dtype,
+                               int out_dtype, float drop_p, const void* seed_dev, void* stream);
+
 /* Frozen conv-weight preparation: src [Cout,Cin,kh,kw] (LB_F32/LB_BF16/LB_F16) ->
  *   dst16  [Cout, kh*kw*Cin]  (tap-major K; forward operand)              and/or
  *   dstT16 [Cin, kh*kw*Cout]  with taps flipped (input-gradient operand). Either may be NULL. */
@@ -233,6 +257,24 @@ int lb_refresh_shadows(const float* p, const long long* table, int n_entries, in
  * dW[b] = Wt[b] - Wb[b] (N x K, row-major, LB_F32/LB_BF16/LB_F16). Wt/Wb are DEVICE arrays of `batch` device pointers to same-shape
  * matrices. Tall-skinny operands are fp32 row-major [batch, rows, 32]. See lora_b200/svd.py for
  * the driver (probe -> power iterations with CholeskyQR2 -> 32x32 Jacobi -> factors). */
+/* SVD distillation of cli_svd.py:24-92 (`overwrite_base`) for ALL sites of a model in one call,
+ * ragged over shapes (SURVEY.md 8b `lora_svd_truncated_batched`): for b < batch,
+ *   dW = Wt[b] - Wb[b]  ([N[b], K[b]] row-major, w_dtype in {LB_F32, LB_BF16, LB_F16}; Wb NULL or
+ *   Wb[b] ignored when the array is NULL: dW = Wt[b]) -> top-`rank` singular triplets by a
+ *   randomized range finder (32 probes, `power_iters` power iterations = 2*power_iters+2 streaming
+ *   passes over both weights, contraction on the tensor cores in 3-term split-bf16) ->
+ *   out[off_b ...] = [ up = U_r diag(S_r) as [N, rank] | down = Vh_r as [rank, K] ] fp32, with
+ *   off_b = rank * sum_{c<b} (N[c] + K[c]); sigma_out[b, 0..31] (descending; may be NULL);
+ *   clamp_q > 0: both factors clamped to +-torch.quantile(cat(up, down), clamp_q) (exact order
+ *   statistics, cli_svd.py:43-47), the threshold reported in hi_out[b] (may be NULL).
+ * All array arguments are HOST arrays; workspace is device memory of at least
+ * lb_svd_workspace_bytes(N, K, batch, w_dtype) bytes. K[b] must keep rows 16-byte aligned. */
+long long lb_svd_workspace_bytes(const int* N, const int* K, int batch, int w_dtype);
+int lb_svd_truncated_batched(const void* const* Wt, const void* const* Wb, const int* N, const int* K,
+                             int batch, int w_dtype, int rank, int power_iters, float clamp_q,
+                             unsigned long long seed, float* out, float* sigma_out, float* hi_out,
+                             void* workspace, long long workspace_bytes, void* stream);
+
 /* transpose = 0: out[b] (N x 32) = dW[b] . in[b] (K x 32);  1: out[b] (K x 32) = dW[b]^T . in[b] (N x 32) */
 int lb_svd_mul(const void* const* Wt, const void* const* Wb, int w_dtype, const float* in, float* out,
                int N, int K, int batch, int transpose, void* stream);

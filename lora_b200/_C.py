@@ -42,6 +42,11 @@ def _load():
         "lb_abi_version": ([], i32),
         "lb_lora_linear_fwd": ([vp, vp, vp, vp, vp, ll, ll, vp, f32, vp, vp, vp,
                                 i32, i32, i32, i32, i32, i32, vp], i32),
+        "lb_lora_linear_fwd_dropout": ([vp, vp, vp, vp, vp, ll, ll, vp, f32, vp, vp,
+                                        i32, i32, i32, i32, i32, i32, f32, vp, vp], i32),
+        "lb_lora_conv2d_fwd_dropout": ([vp, vp, vp, vp, vp, ll, ll, vp, f32, vp, vp,
+                                        i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32,
+                                        f32, vp, vp], i32),
         "lb_lora_wgrad": ([vp, vp, vp, f32, vp, ll, ll, i32, i32, i32, i32, vp], i32),
         "lb_cast_rows_pad16": ([vp, ll, ll, vp, i32, i32, i32, vp], i32),
         "lb_cast_weight": ([vp, i32, vp, vp, i32, i32, i32, vp], i32),
@@ -60,6 +65,9 @@ def _load():
         "lb_debug_set_pdl": ([i32], i32),
         "lb_lora_wgrad_pair": ([vp, vp, vp, ll, ll, i32, vp, vp, vp, ll, ll, i32, vp, f32, i32, i32,
                                 f32, vp, i32, vp], i32),
+        "lb_svd_workspace_bytes": ([ctypes.POINTER(i32), ctypes.POINTER(i32), i32, i32], ll),
+        "lb_svd_truncated_batched": ([vp, vp, ctypes.POINTER(i32), ctypes.POINTER(i32), i32, i32, i32, i32, f32,
+                                      ctypes.c_ulonglong, vp, vp, vp, vp, ll, vp], i32),
         "lb_svd_mul": ([vp, vp, i32, vp, vp, i32, i32, i32, i32, vp], i32),
         "lb_svd_gram": ([vp, vp, i32, i32, vp], i32),
         "lb_svd_chol_inv": ([vp, vp, i32, vp], i32),
@@ -109,7 +117,8 @@ EXPORTED = [n for n in ("lb_abi_version", "lb_lora_linear_fwd", "lb_lora_wgrad",
                         "lb_refresh_shadows", "lb_lora_wgrad_shift", "lb_lora_conv2d_fwd",
                         "lb_cast_conv_weight", "lb_lora_up_dropout", "lb_lora_dropout_dt",
                         "lb_lora_wgrad_masked", "lb_lora_wgrad_pair", "lb_svd_mul", "lb_svd_gram",
-                        "lb_svd_chol_inv", "lb_svd_apply", "lb_svd_jacobi", "lb_svd_randn", "lb_split_bf16x3", "lb_lora_merge", "lb_ti_embed_step", "lb_lora_linear_fwd_grouped", "lb_lora_wgrad_multi", "lb_lora_wgrad_conv")]
+                        "lb_svd_chol_inv", "lb_svd_apply", "lb_svd_jacobi", "lb_svd_randn", "lb_split_bf16x3", "lb_lora_merge", "lb_ti_embed_step", "lb_lora_linear_fwd_grouped", "lb_lora_wgrad_multi", "lb_lora_wgrad_conv",
+                        "lb_lora_linear_fwd_dropout", "lb_lora_conv2d_fwd_dropout", "lb_debug_set_pdl", "lb_svd_workspace_bytes", "lb_svd_truncated_batched")]
 
 
 def check(status: int, what: str):

@@ -22,6 +22,7 @@
 // acc += T'_g . U_g^T (K = 16 each) into the same TMEM accumulator. Bias is added in the epilogue
 // and the tile leaves through a swizzled staging buffer and TMA stores.
 #pragma once
+#include "dropmask.cuh"
 #include "ptx.cuh"
 
 namespace lb {
@@ -51,6 +52,18 @@ struct FusedParams {
   int kh, kw, pad_h, pad_w;
   int TH, TW, tiles_h, tiles_w;
   int down_per_tap;    // 1: D columns advance with the tap (forward); 0: D restarts every tap (dX)
+  // dropout on the LoRA branch (DROP kernels only): keep(m, n) from dropmask.cuh on element index
+  // row * N + n, survivors scaled by drop_inv = 1/(1-p); seed lives in device memory (graph-safe)
+  float drop_p, drop_inv;
+  const unsigned long long* seed;
+  // split-K (SPLITK kernels only): gridDim.z = split CTAs share one output tile, each reducing a
+  // contiguous range of K blocks; partial accumulators ([split][128][BLOCK_N + 16 G] fp32 per tile)
+  // go through `ws` (L2-resident), `counters[tile]` elects the last CTA to arrive, which adds the
+  // other partials to its own TMEM accumulator and runs the ordinary epilogue. Counters must be 0
+  // on entry and are reset by the elected CTA.
+  int split;
+  float* ws;
+  unsigned int* counters;
   unsigned long long* dbg;  // profiling only: 16 x %globaltimer stamps written by CTA (0,0), or null
 };
 
@@ -61,7 +74,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #define LB_STAMP(i) do { if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[i] = gtimer(); } while (0)
 
-template <int BLOCK_N, int STAGES, typename OutT, int G>
+template <int BLOCK_N, int STAGES, typename OutT, int G, bool DROP = false>
 struct Smem {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = (BLOCK_N + R_PAD) * BLOCK_K * 2;
@@ -84,18 +97,22 @@ struct Smem {
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
-  static constexpr int ACC_COLS = BLOCK_N + R_PAD * G;
+  // DROP: the LoRA product T'.U^T gets its own BLOCK_N TMEM columns (the mask sits between it
+  // and the sum, so it cannot be accumulated into the base)
+  static constexpr int L_COL0 = BLOCK_N + R_PAD * G;
+  static constexpr int ACC_COLS = BLOCK_N + R_PAD * G + (DROP ? BLOCK_N : 0);
   static constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);
   static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
   static_assert(ACC_COLS <= 512, "TMEM budget exceeded");
 };
 
 // One output tile (n_blk, m_blk) of one problem; called by the single-problem and the grouped kernel.
-template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G>
+template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G, bool DROP = false, bool SPLITK = false>
 __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtensorMap& tmW,
                                            const CUtensorMap& tmD, const CUtensorMap& tmY,
                                            const FusedParams& p, const int n_blk, const int m_blk) {
-  using S = Smem<BLOCK_N, STAGES, OutT, G>;
+  using S = Smem<BLOCK_N, STAGES, OutT, G, DROP>;
+  constexpr int PCOLS = BLOCK_N + R_PAD * G;          // columns of one partial accumulator
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));  // generic pointer to the aligned base
@@ -117,6 +134,9 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
   const int taps = CONV ? p.kh * p.kw : 1;
   const int cblocks = CONV ? (p.C + BLOCK_K - 1) / BLOCK_K : (p.K + BLOCK_K - 1) / BLOCK_K;
   const int num_kb = taps * cblocks;
+  // this CTA's share of the K loop (split-K: blockIdx.z of gridDim.z; launcher keeps split <= num_kb)
+  const int kb_begin = SPLITK ? static_cast<int>((static_cast<long long>(blockIdx.z) * num_kb) / p.split) : 0;
+  const int kb_end = SPLITK ? static_cast<int>((static_cast<long long>(blockIdx.z + 1) * num_kb) / p.split) : num_kb;
 
   auto bar_full = [&](int s) { return sbase + S::OFF_BAR + 8 * s; };
   auto bar_empty = [&](int s) { return sbase + S::OFF_BAR + 8 * (STAGES + s); };
@@ -160,9 +180,10 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       LB_STAMP(1);                       // first TMA about to be issued
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int it = kb - kb_begin;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(bar_empty(s), ph ^ 1);
         mbar_expect_tx(bar_full(s), S::STAGE_BYTES);
         const uint32_t sa = sbase + s * S::STAGE_BYTES;
@@ -187,26 +208,28 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
       const uint32_t idesc_wide = umma_idesc_f16(p.fmt, BLOCK_M, BLOCK_N + R_PAD);
       const uint32_t idesc_base = umma_idesc_f16(p.fmt, BLOCK_M, BLOCK_N);
       const uint32_t idesc_t = umma_idesc_f16(p.fmt, BLOCK_M, R_PAD);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int it = kb - kb_begin;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(bar_full(s), ph);
-        if (kb == 0) LB_STAMP(2);          // first stage landed
+        if (it == 0) LB_STAMP(2);          // first stage landed
         tc_fence_after();
         const uint32_t sa = sbase + s * S::STAGE_BYTES;
         const uint32_t sb = sa + S::A_BYTES;
         const int tap = (G > 1) ? kb / cblocks : 0;
-        const bool tap_first = (G > 1) ? (kb - tap * cblocks) == 0 : false;
+        // first K block this CTA feeds into the tap's T columns (a split range may start mid-tap)
+        const bool tap_first = (G > 1) ? ((kb - tap * cblocks) == 0 || it == 0) : false;
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
           // K-major SWIZZLE_128B: 8-row groups 1024 B apart; one K-step = 32 B along the row
           const uint64_t ad = umma_smem_desc(sa + k * UMMA_K * 2, 16, 1024, 2);
           const uint64_t bd = umma_smem_desc(sb + k * UMMA_K * 2, 16, 1024, 2);
           if constexpr (G == 1) {
-            umma_f16_ss(tmem, ad, bd, idesc_wide, (kb | k) != 0);
+            umma_f16_ss(tmem, ad, bd, idesc_wide, (it | k) != 0);
           } else {
             const uint64_t dd = umma_smem_desc(sb + BLOCK_N * 128 + k * UMMA_K * 2, 16, 1024, 2);
-            umma_f16_ss(tmem, ad, bd, idesc_base, (kb | k) != 0);
+            umma_f16_ss(tmem, ad, bd, idesc_base, (it | k) != 0);
             umma_f16_ss(tmem + BLOCK_N + R_PAD * tap, ad, dd, idesc_t, !(tap_first && k == 0));
           }
         }
@@ -218,13 +241,19 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
       mbar_wait(bar_tready, 0);
       LB_STAMP(5);                         // T' operand visible to the MMA warp
       tc_fence_after();
+      // split-K: only the elected CTA continues (the others have stored their partial and leave)
+      const bool go = SPLITK ? (*reinterpret_cast<volatile uint32_t*>(sgen + S::OFF_TMEM + 4) != 0u) : true;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
+        if (!go) break;
         // no-swizzle K-major operand of total K = 16 G: core matrix = 8 rows x 16 B (128 B
         // contiguous); LBO = 128 B (next K core matrix), SBO = 256 G bytes (next 8-row group)
         const uint64_t ad = umma_smem_desc(sbase + S::OFF_T + g * 256, 128, 256 * G, 0);
         const uint64_t bd = umma_smem_desc(sbase + S::OFF_UP + g * 256, 128, 256 * G, 0);
-        umma_f16_ss(tmem, ad, bd, idesc_base, 1);
+        if constexpr (DROP)
+          umma_f16_ss(tmem + S::L_COL0, ad, bd, idesc_base, g != 0);   // own columns (masked in the drain)
+        else
+          umma_f16_ss(tmem, ad, bd, idesc_base, 1);
       }
       umma_commit(bar_final);
     }
@@ -271,15 +300,92 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
     mbar_wait(bar_acc, 0);
     if (et == 0) LB_STAMP(4);            // main-loop MMAs completed (accumulator ready)
     tc_fence_after();
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
+    bool elected = true;          // split-K: is this the CTA that finishes the tile?
+    const float* peers = nullptr; // split-K: this tile's [split][128][PCOLS] partials
+    int my_rank = 0;
+    auto tap_touched = [&](int g) {   // did this CTA's K range feed tap g's T columns?
+      return !SPLITK || G == 1 || (kb_begin < (g + 1) * cblocks && kb_end > g * cblocks);
+    };
+    // sum of the OTHER CTAs' partials for 16 columns of this thread's row (L2 reads, 4 peers in flight)
+    auto add_peers16 = [&](float (&acc)[16], int col0) {
+      for (int s0 = 0; s0 < p.split; s0 += 4) {
+        float4 buf[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int sp = s0 + u;
+          const bool ok = sp < p.split && sp != my_rank;
+          const float4* src = reinterpret_cast<const float4*>(
+              peers + (static_cast<size_t>(ok ? sp : 0) * BLOCK_M + row) * PCOLS + col0);
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) buf[u][w4] = ok ? __ldcg(src + w4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) {
+            acc[4 * w4 + 0] += buf[u][w4].x; acc[4 * w4 + 1] += buf[u][w4].y;
+            acc[4 * w4 + 2] += buf[u][w4].z; acc[4 * w4 + 3] += buf[u][w4].w;
+          }
+      }
+    };
+    if constexpr (SPLITK) {
+      my_rank = blockIdx.z;
+      const unsigned tile_id = blockIdx.y * gridDim.x + blockIdx.x;
+      float* tile_ws = p.ws + static_cast<size_t>(tile_id) * p.split * (BLOCK_M * PCOLS);
+      peers = tile_ws;
+      float* mine = tile_ws + (static_cast<size_t>(my_rank) * BLOCK_M + row) * PCOLS;
+      // own partial -> workspace, 16 columns at a time (T columns of taps this CTA never fed: zeros)
+#pragma unroll 1
+      for (int c = 0; c < PCOLS / 16; ++c) {
+        uint32_t v[16];
+        const bool live = c < BLOCK_N / 16 || tap_touched(c - BLOCK_N / 16);
+        if (live) {
+          tmem_ld16(lane_base + c * 16, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+        float4* dst = reinterpret_cast<float4*>(mine + c * 16);
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4)
+          dst[w4] = make_float4(__uint_as_float(v[4 * w4]), __uint_as_float(v[4 * w4 + 1]),
+                                __uint_as_float(v[4 * w4 + 2]), __uint_as_float(v[4 * w4 + 3]));
+      }
+      __threadfence();                               // partial visible device-wide before the count
+      named_bar_sync(1, EPI_THREADS);
+      volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(sgen + S::OFF_TMEM + 4);
+      if (et == 0) {
+        const unsigned old = atomicAdd(p.counters + tile_id, 1u);
+        const bool last = old == static_cast<unsigned>(p.split - 1);
+        if (last) p.counters[tile_id] = 0u;           // ready for the next launch on this stream
+        *flag = last ? 1u : 0u;
+        __threadfence();
+      }
+      named_bar_sync(1, EPI_THREADS);
+      elected = *flag != 0u;
+      if (!elected) {                                 // partial delivered: release the MMA warp and leave
+        tc_fence_before();
+        mbar_arrive(bar_tready);
+      }
+    }
+    if (elected) {
 #pragma unroll
     for (int g = 0; g < G; ++g) {
       float t[R_PAD];
       if (p.t_in == nullptr) {
-        uint32_t tv[R_PAD];
-        tmem_ld16(tmem + (static_cast<uint32_t>(q * 32) << 16) + BLOCK_N + R_PAD * g, tv);
-        tmem_ld_wait();
+        if (tap_touched(g)) {
+          uint32_t tv[R_PAD];
+          tmem_ld16(lane_base + BLOCK_N + R_PAD * g, tv);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < R_PAD; ++j) t[j] = __uint_as_float(tv[j]);
+          for (int j = 0; j < R_PAD; ++j) t[j] = __uint_as_float(tv[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < R_PAD; ++j) t[j] = 0.f;
+        }
+        if constexpr (SPLITK) add_peers16(t, BLOCK_N + R_PAD * g);
       } else {
         long long srow = grow;
         if constexpr (CONV && G > 1) {   // group g = tap g: the pixel shifted by (dy - pad, dx - pad)
@@ -322,14 +428,44 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
     mbar_wait(bar_final, 0);
     if (et == 0) LB_STAMP(6);            // LoRA MMA completed
     tc_fence_after();
+    uint32_t ds0 = 0, ds1 = 0, dthr = 0;
+    if constexpr (DROP) {
+      const unsigned long long sd = __ldg(p.seed);
+      ds0 = static_cast<uint32_t>(sd);
+      ds1 = static_cast<uint32_t>(sd >> 32);
+      dthr = drop_threshold(p.drop_p);
+    }
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N / 32; ++c) {
       uint32_t v[32];
-      tmem_ld32(tmem + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
+      tmem_ld32(lane_base + c * 32, v);
       float f[32];
+      uint32_t lv[DROP ? 32 : 1];
+      if constexpr (DROP) tmem_ld32(lane_base + S::L_COL0 + c * 32, lv);
+      tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_s[c * 32 + j];
+      if constexpr (SPLITK) {
+        float lo16[16], hi16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { lo16[j] = f[j]; hi16[j] = f[16 + j]; }
+        add_peers16(lo16, c * 32);
+        add_peers16(hi16, c * 32 + 16);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { f[j] = lo16[j]; f[16 + j] = hi16[j]; }
+      }
+      if constexpr (DROP) {
+        // element index row*N + n; N % 8 == 0 and the chunk starts at a multiple of 32, so the
+        // chunk's first element is even: 16 pair-hashes cover its 32 columns
+        const unsigned long long e0 =
+            (static_cast<unsigned long long>(grow < 0 ? 0 : grow) * p.N + n0 + c * 32) >> 1;
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const uint32_t bits = drop_bits(ds0, ds1, e0 + jj);
+          if ((bits & 0xffffu) >= dthr) f[2 * jj] += __uint_as_float(lv[2 * jj]) * p.drop_inv;
+          if ((bits >> 16) >= dthr) f[2 * jj + 1] += __uint_as_float(lv[2 * jj + 1]) * p.drop_inv;
+        }
+      }
       if constexpr (sizeof(OutT) == 2) {
         const int box = c >> 1;
         const uint32_t rbase = sbase + S::OFF_OUT + box * S::BOX_BYTES + row * 128;
@@ -369,6 +505,7 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
       tma_store_wait_read0();
       LB_STAMP(8);                       // staging buffer released
     }
+    }  // elected
   }
 
   __syncthreads();
@@ -379,12 +516,13 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
   if (threadIdx.x == 32) LB_STAMP(9);    // kernel exit
 }
 
-template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G, int MIN_CTAS = 1>
+template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G, int MIN_CTAS = 1, bool DROP = false,
+          bool SPLITK = false>
 __global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
 fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY,
                   const FusedParams p) {
-  fused_tile<BLOCK_N, STAGES, OutT, CONV, G>(tmX, tmW, tmD, tmY, p, blockIdx.x, blockIdx.y);
+  fused_tile<BLOCK_N, STAGES, OutT, CONV, G, DROP, SPLITK>(tmX, tmW, tmD, tmY, p, blockIdx.x, blockIdx.y);
 }
 
 // Several same-dtype linear problems in ONE launch (sites that share an input: q/k/v of an

@@ -9,11 +9,20 @@
 
 namespace lb {
 
-template <int BLOCK_N, int STAGES, typename OutT, int MIN_CTAS>
-static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, const FusedParams& p,
-                         int out_dtype, cudaStream_t stream) {
-  using S = Smem<BLOCK_N, STAGES, OutT, 1>;
-  auto kern = fused_lora_kernel<BLOCK_N, STAGES, OutT, false, 1, MIN_CTAS>;
+template <int BLOCK_N, int STAGES, typename OutT, int MIN_CTAS, bool DROP = false, bool SPLITK = false>
+static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, const FusedParams& p_in,
+                         int out_dtype, cudaStream_t stream, int split = 1) {
+  using S = Smem<BLOCK_N, STAGES, OutT, 1, DROP>;
+  auto kern = fused_lora_kernel<BLOCK_N, STAGES, OutT, false, 1, MIN_CTAS, DROP, SPLITK>;
+  FusedParams p = p_in;
+  p.split = 1;
+  if constexpr (SPLITK) {
+    const size_t tiles = static_cast<size_t>((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + BLOCK_M - 1) / BLOCK_M);
+    p.split = split;
+    if (!split_ws_reserve(stream, tiles * split * BLOCK_M * (BLOCK_N + R_PAD) * sizeof(float),
+                          static_cast<unsigned int>(tiles), &p.ws, &p.counters))
+      return LB_ERR_CUDA;
+  }
   static_assert(MIN_CTAS * (S::DYN_BYTES + 1024) <= 233472 && MIN_CTAS * S::TMEM_COLS <= 512, "occupancy target does not fit");
   static unsigned long long attr_mask = 0;
   if (!ensure_dyn_smem(reinterpret_cast<const void*>(kern), S::DYN_BYTES, attr_mask)) return LB_ERR_CUDA;
@@ -24,9 +33,39 @@ static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, 
   if (!tmap_2d(&tmW, W, in_dt, 2, p.K, p.N, BLOCK_K, BLOCK_N, true)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmD, Dn, in_dt, 2, p.K, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmY, Y, out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
-  dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M, 1);
+  dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M, SPLITK ? split : 1);
   return launch_ex(kern, dim3(grid), dim3(NUM_THREADS), S::DYN_BYTES, stream, 1, tmX, tmW, tmD, tmY, p) == cudaSuccess
              ? LB_OK : LB_ERR_CUDA;
+}
+
+// Split-K plan for one linear problem (fused_core.cuh, SPLITK): the per-SM operand ingest (~92 GB/s
+// measured) makes a lone CTA's K loop cost ~0.29 us (BLOCK_N 64) / ~0.38 us (128) per
+// 64-wide K block, so sites with few tiles and long K leave most SMs idle while a handful stream.
+// Cost model in microseconds: fixed 2.0 (prologue + tail) + blocks x ingest; a split adds ~1.0
+// (publish + election) + the elected CTA's reads of the other partials (fp32, same ingest limit).
+// Only single-wave plans (tiles x split <= SMs) are considered, and a split must win by > 15 %.
+struct SplitPlan { int block_n, split; };
+static SplitPlan plan_split(int M, int K, int N, int n_sms) {
+  if (!splitk_enabled() || n_sms <= 0) return {0, 1};
+  const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  SplitPlan best = {0, 1};
+  double best_t = 1e30, base_t = 1e30;
+  for (int bn = 64; bn <= 128; bn += 64) {
+    const long long tiles = static_cast<long long>(m_tiles) * ((N + bn - 1) / bn);
+    const double per_kb = (128.0 + bn + 16.0) * 128.0 / 92e3;
+    const double waves = static_cast<double>((tiles + n_sms - 1) / n_sms);
+    const double t1 = waves * (2.0 + num_kb * per_kb);
+    if (t1 < base_t) base_t = t1;
+    for (int sp = 2; sp <= 8; ++sp) {
+      if (tiles * sp > n_sms || num_kb / sp < 4) break;
+      const double peer = (bn + 16.0) * 512.0 / 92e3;
+      const double t = 2.0 + ((num_kb + sp - 1) / sp) * per_kb + 1.0 + (sp - 1) * peer;
+      if (t < best_t) { best_t = t; best = {bn, sp}; }
+    }
+  }
+  if (best.split > 1 && best_t < 0.85 * base_t) return best;
+  return {0, 1};
 }
 
 template <int BLOCK_N, int STAGES, typename OutT>
@@ -125,12 +164,15 @@ extern "C" int lb_debug_set_stamp_buffer(void* dev_buf) {
   return LB_OK;
 }
 
-extern "C" int lb_lora_linear_fwd(const void* X, const void* W, const float* bias,
+static int linear_fwd_impl(const void* X, const void* W, const float* bias,
                                   const void* down16, const float* up, long long up_rs,
                                   long long up_cs, const float* diag, float scale, void* Y,
                                   float* T_out, const float* T_in, int M, int K, int N, int r,
-                                  int in_dtype, int out_dtype, void* stream) {
+                                  int in_dtype, int out_dtype, float drop_p, const void* seed_dev,
+                                  void* stream) {
   using namespace lb;
+  if (!(drop_p >= 0.f && drop_p < 1.f) || (drop_p > 0.f && (seed_dev == nullptr || T_in != nullptr)))
+    return LB_ERR_SHAPE;
   if (M <= 0 || N <= 0 || K <= 0) return LB_ERR_SHAPE;
   if (r < 1 || r > R_PAD) return LB_ERR_RANK;
   if (in_dtype != LB_BF16 && in_dtype != LB_F16) return LB_ERR_DTYPE;
@@ -147,8 +189,40 @@ extern "C" int lb_lora_linear_fwd(const void* X, const void* W, const float* bia
   p.bias = bias; p.up = up; p.up_rs = up_rs; p.up_cs = up_cs; p.up_gs = 0; p.diag = diag;
   p.t_out = T_out; p.t_in = T_in; p.scale = scale; p.M = M; p.N = N; p.K = K; p.r = r;
   p.fmt = (in_dtype == LB_BF16) ? 1 : 0; p.t_group = 0; p.dbg = g_dbg;
+  p.drop_p = drop_p; p.drop_inv = 1.f / (1.f - drop_p);
+  p.seed = reinterpret_cast<const unsigned long long*>(seed_dev);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (drop_p > 0.f) {
+    // Dropout on the branch: the LoRA product keeps its own TMEM columns and is masked in the
+    // drain (fused_core.cuh, DROP). One tile per CTA; BLOCK_N 64 (256 TMEM columns, 2 CTAs/SM)
+    // unless the site has plenty of 128-wide tiles.
+    const SplitPlan spd = plan_split(M, K, N, sm_count());
+    if (spd.split > 1) {
+      if (out_dtype == LB_F32)
+        return spd.block_n == 64 ? launch_linear<64, 4, float, 1, true, true>(X, W, down16, Y, p, out_dtype, st, spd.split)
+                                 : launch_linear<128, 4, float, 1, true, true>(X, W, down16, Y, p, out_dtype, st, spd.split);
+      return spd.block_n == 64 ? launch_linear<64, 5, uint16_t, 1, true, true>(X, W, down16, Y, p, out_dtype, st, spd.split)
+                               : launch_linear<128, 4, uint16_t, 1, true, true>(X, W, down16, Y, p, out_dtype, st, spd.split);
+    }
+    const long long t128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
+    const bool nar = t128 < 120 && !(K >= 2048 && t128 >= 64);
+    if (out_dtype == LB_F32)
+      return nar ? launch_linear<64, 3, float, 2, true>(X, W, down16, Y, p, out_dtype, st)
+                 : launch_linear<128, 4, float, 1, true>(X, W, down16, Y, p, out_dtype, st);
+    return nar ? launch_linear<64, 3, uint16_t, 2, true>(X, W, down16, Y, p, out_dtype, st)
+               : launch_linear<128, 4, uint16_t, 1, true>(X, W, down16, Y, p, out_dtype, st);
+  }
 
+  if ((g_linear_mode & 3) == 0) {
+    const SplitPlan sp = plan_split(M, K, N, sm_count());
+    if (sp.split > 1) {
+      if (out_dtype == LB_F32)
+        return sp.block_n == 64 ? launch_linear<64, 5, float, 1, false, true>(X, W, down16, Y, p, out_dtype, st, sp.split)
+                                : launch_linear<128, 4, float, 1, false, true>(X, W, down16, Y, p, out_dtype, st, sp.split);
+      return sp.block_n == 64 ? launch_linear<64, 6, uint16_t, 1, false, true>(X, W, down16, Y, p, out_dtype, st, sp.split)
+                              : launch_linear<128, 4, uint16_t, 1, false, true>(X, W, down16, Y, p, out_dtype, st, sp.split);
+    }
+  }
   const int sched = g_linear_mode & 3, bn_choice = (g_linear_mode >> 2) & 3, split_choice = g_linear_mode >> 4;
   const long long tiles128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
   bool narrow = tiles128 < 120;  // not enough 128-wide tiles to fill 148 SMs: halve BLOCK_N
@@ -201,6 +275,24 @@ extern "C" int lb_lora_linear_fwd(const void* X, const void* W, const float* bia
                  : launch_linear<128, 4, uint16_t, 1>(X, W, down16, Y, p, out_dtype, st);
 }
 
+
+extern "C" int lb_lora_linear_fwd(const void* X, const void* W, const float* bias,
+                                  const void* down16, const float* up, long long up_rs,
+                                  long long up_cs, const float* diag, float scale, void* Y,
+                                  float* T_out, const float* T_in, int M, int K, int N, int r,
+                                  int in_dtype, int out_dtype, void* stream) {
+  return linear_fwd_impl(X, W, bias, down16, up, up_rs, up_cs, diag, scale, Y, T_out, T_in, M, K, N, r,
+                         in_dtype, out_dtype, 0.f, nullptr, stream);
+}
+
+extern "C" int lb_lora_linear_fwd_dropout(const void* X, const void* W, const float* bias,
+                                          const void* down16, const float* up, long long up_rs,
+                                          long long up_cs, const float* diag, float scale, void* Y,
+                                          float* T_out, int M, int K, int N, int r, int in_dtype,
+                                          int out_dtype, float drop_p, const void* seed_dev, void* stream) {
+  return linear_fwd_impl(X, W, bias, down16, up, up_rs, up_cs, diag, scale, Y, T_out, nullptr, M, K, N, r,
+                         in_dtype, out_dtype, drop_p, seed_dev, stream);
+}
 
 extern "C" int lb_lora_linear_fwd_grouped(int n, const void* const* X, const void* const* W,
                                           const float* const* bias, const void* const* down16,

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "dropmask.cuh"
 #include "lora_b200.h"
 
 namespace lb {
@@ -30,19 +31,6 @@ __device__ __forceinline__ uint16_t to16(float x, int fmt) {
 __device__ __forceinline__ float from16(uint16_t x, int fmt) {
   if (fmt) return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&x));
   return __half2float(*reinterpret_cast<__half*>(&x));
-}
-
-// ------------------------------------------------------------------------------- dropout mask
-// Counter-based keep decision for element `idx` of the LoRA-branch output (nn.Dropout,
-// lora.py:45,56): a splitmix64 finaliser of (seed + idx * golden). Forward and the three backward
-// kernels recompute the same bit from (seed, idx); nothing is stored. The stream differs from
-// ATen's Philox, so parity with the reference under dropout is statistical.
-__device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long long idx, float p) {
-  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return static_cast<float>(z >> 40) * (1.0f / 16777216.0f) >= p;
 }
 
 // ------------------------------------------------------------------------------- wgrad
@@ -530,7 +518,7 @@ ti_step_kernel(float* __restrict__ rows, float* __restrict__ grad, float* __rest
 // =============================================================================== C ABI
 using namespace lb;
 
-extern "C" int lb_abi_version(void) { return 2; }
+extern "C" int lb_abi_version(void) { return 3; }
 
 extern "C" int lb_lora_wgrad_shift(const void* S, const float* V, const float* diag, float scale,
                                    float* out, long long out_js, long long out_cs, int M, int C,

@@ -1,0 +1,860 @@
+// lb_svd_truncated_batched: the whole SVD distillation of /root/reference/lora_diffusion/cli_svd.py:24-92
+// (`overwrite_base`: per site  dW = W_tuned - W_base -> SVD -> U_r diag(S_r), Vh_r -> quantile clamp)
+// for ALL sites of a model in one C call, ragged over shapes.
+//
+// Algorithm (per matrix, all matrices in flight together): randomized range finder with L = 32
+// Rademacher probes and q power iterations, then the exact SVD of the projected 32 x K problem:
+//     Y = dW Om ; [ Z = dW^T orth(Y) ; Y = dW orth(Z) ] x q ; Q = orth2(Y) ; B^T = dW^T Q ;
+//     B B^T = Uh diag(s^2) Uh^T ;  up = Q Uh_r diag(s_r) ;  down = diag(1/s_r) Uh_r^T B
+// = 2q + 2 streaming passes over (W_tuned, W_base); dW is formed in registers and never stored.
+// orth() = Gram matrix -> 32 x 32 Jacobi eigen-decomposition -> multiply by V diag(1/s)
+// (rank-revealing: numerically null directions become zero columns -- an exactly low-rank delta,
+// i.e. a merged LoRA, is a real input).
+//
+// Kernels:
+//   mul_right / mul_left   the passes. HBM-bound: AI = 2*32 flop per 4 bytes = 16 flop/B, i.e.
+//       ~105 TFLOP/s at the 6.6 TB/s roofline -- beyond the fp32 CUDA cores (72 TFLOP/s), so the
+//       contraction runs on the tensor cores: the fp32 delta tile is split in registers into
+//       bf16 hi + lo, the tall-skinny operand likewise, and hi.hi + lo.hi + hi.lo are accumulated
+//       in fp32 with mma.sync.m16n8k16 (2^-16 relative per product: fp32-faithful; tcgen05 would
+//       need the operands staged in UMMA shared-memory layouts and buys nothing on a memory-bound
+//       pass). Weights come in through 16-byte vector loads, one tile ahead in registers.
+//   mul_right also accumulates the Gram matrix of its output tile (no separate pass over Y).
+//   tall_transform         Y <- Y V diag(1/s) (+ Gram of the result), or Gram only
+//   jacobi32               block-wide cyclic Jacobi, 16 disjoint rotations per step in parallel
+//   factors                up / down from (Q, B^T, Uh, s)
+//   quantile_clamp         exact radix select of torch.quantile's two order statistics over
+//                          cat(up, down) (cli_svd.py:43-47), lerp, symmetric clamp, in place
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "lora_b200.h"
+
+namespace lbsvd2 {
+
+constexpr int L = 32;     // probe / subspace width
+constexpr int TM = 128;   // rows of a weight tile
+constexpr int THREADS = 256;
+
+struct MatDesc {
+  const void* wt;
+  const void* wb;          // may be null (dW = W_tuned)
+  int N, K;
+  long long yoff;          // first row of this matrix in the [sum N, 32] workspace
+  long long zoff;          // first row in the [sum K, 32] workspace
+  long long out_off;       // element offset of [up (N x r) | down (r x K)] in the flat fp32 output
+};
+struct RItem { int b, row0; };            // mul_right: one 128-row block of matrix b
+struct LItem { int b, k0, n0, n1; };      // mul_left : one KT-column block x row slab [n0, n1)
+struct TItem { int b, row0; };            // tall kernels: one 256-row block
+
+// ------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint4 ldg16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t (&r)[2]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// fp32 pair -> (bf16 hi pair, bf16 lo pair); x = hi + lo + O(2^-16 |x|)
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 hx = __float2bfloat16_rn(x), hy = __float2bfloat16_rn(y);
+  const __nv_bfloat16 lx = __float2bfloat16_rn(x - __bfloat162float(hx));
+  const __nv_bfloat16 ly = __float2bfloat16_rn(y - __bfloat162float(hy));
+  hi = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&hx)) |
+       (static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&hy)) << 16);
+  lo = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&lx)) |
+       (static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&ly)) << 16);
+}
+
+template <typename WT> struct WTraits;
+template <> struct WTraits<__half> {
+  static constexpr int KT = 64, VEC = 8;
+  static __device__ __forceinline__ void diff(const uint4& t, const uint4& b, float (&d)[8]) {
+    const __half2* a = reinterpret_cast<const __half2*>(&t);
+    const __half2* c = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __half22float2(a[i]), y = __half22float2(c[i]);
+      d[2 * i] = x.x - y.x; d[2 * i + 1] = x.y - y.y;
+    }
+  }
+};
+template <> struct WTraits<__nv_bfloat16> {
+  static constexpr int KT = 64, VEC = 8;
+  static __device__ __forceinline__ void diff(const uint4& t, const uint4& b, float (&d)[8]) {
+    const __nv_bfloat162* a = reinterpret_cast<const __nv_bfloat162*>(&t);
+    const __nv_bfloat162* c = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = __bfloat1622float2(a[i]), y = __bfloat1622float2(c[i]);
+      d[2 * i] = x.x - y.x; d[2 * i + 1] = x.y - y.y;
+    }
+  }
+};
+template <> struct WTraits<float> {
+  static constexpr int KT = 32, VEC = 4;
+  static __device__ __forceinline__ void diff(const uint4& t, const uint4& b, float (&d)[4]) {
+    d[0] = __uint_as_float(t.x) - __uint_as_float(b.x);
+    d[1] = __uint_as_float(t.y) - __uint_as_float(b.y);
+    d[2] = __uint_as_float(t.z) - __uint_as_float(b.z);
+    d[3] = __uint_as_float(t.w) - __uint_as_float(b.w);
+  }
+};
+
+// A [rows x KT] bf16 tile in shared memory: row pitch KT*2 bytes (128 or 64), 16-byte chunks
+// XOR-swizzled so that both ldmatrix (8 rows, same chunk) and the 16-byte row stores are
+// bank-conflict free. Also used for the [k or n][32] tall-skinny chunks (pitch 64 bytes).
+template <int KT>
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
+  if constexpr (KT == 64) return row * 128 + ((chunk ^ (row & 7)) << 4);
+  else return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
+}
+
+// One thread's share of a [128 x KT] weight tile: row = tid/2, columns [half*KT/2, +KT/2) of both
+// weights = 4 x 16 bytes each, fetched one tile ahead of the MMAs that consume it.
+template <typename WT>
+struct TileRegs {
+  uint4 t[4], b[4];
+};
+template <typename WT>
+__device__ __forceinline__ void load_tile(TileRegs<WT>& r, const MatDesc& m, int n, int k_first) {
+  constexpr int VEC = WTraits<WT>::VEC;
+  const bool row_ok = n < m.N;
+  const WT* wt = reinterpret_cast<const WT*>(m.wt) + static_cast<size_t>(n) * m.K;
+  const WT* wb = m.wb ? reinterpret_cast<const WT*>(m.wb) + static_cast<size_t>(n) * m.K : nullptr;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int k = k_first + i * VEC;
+    const bool ok = row_ok && k + VEC <= m.K;
+    r.t[i] = ok ? ldg16(wt + k) : make_uint4(0u, 0u, 0u, 0u);
+    r.b[i] = (ok && wb) ? ldg16(wb + k) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+template <typename WT>
+__device__ __forceinline__ void store_tile(const TileRegs<WT>& r, uint32_t s_hi, uint32_t s_lo, int row, int half) {
+  constexpr int KT = WTraits<WT>::KT;
+  if constexpr (sizeof(WT) == 2) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float d[8];
+      WTraits<WT>::diff(r.t[i], r.b[i], d);
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split2(d[2 * j], d[2 * j + 1], h[j], l[j]);
+      const uint32_t off = tile_off<KT>(row, half * 4 + i);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float d0[4], d1[4];
+      WTraits<WT>::diff(r.t[2 * i], r.b[2 * i], d0);
+      WTraits<WT>::diff(r.t[2 * i + 1], r.b[2 * i + 1], d1);
+      uint32_t h[4], l[4];
+      split2(d0[0], d0[1], h[0], l[0]); split2(d0[2], d0[3], h[1], l[1]);
+      split2(d1[0], d1[1], h[2], l[2]); split2(d1[2], d1[3], h[3], l[3]);
+      const uint32_t off = tile_off<KT>(row, half * 2 + i);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+    }
+  }
+}
+
+// 8 consecutive fp32 of one row of a [rows, 32] tall-skinny operand -> one 16-byte chunk (hi, lo)
+__device__ __forceinline__ void store_tall8(const float4& a, const float4& b, uint32_t s_hi, uint32_t s_lo,
+                                            int row, int chunk) {
+  uint32_t h[4], l[4];
+  split2(a.x, a.y, h[0], l[0]); split2(a.z, a.w, h[1], l[1]);
+  split2(b.x, b.y, h[2], l[2]); split2(b.z, b.w, h[3], l[3]);
+  const uint32_t off = tile_off<32>(row, chunk);
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+}
+
+// ------------------------------------------------------------------------------------ Y = dW . Z
+// CTA = one 128-row block of one matrix, K walked in KT-column steps. Warp w owns rows
+// [16w, 16w+16) x all 32 columns (4 n8 tiles). Optional fused Gram of the output tile.
+template <typename WT>
+__global__ void __launch_bounds__(THREADS, 2)
+mul_right_kernel(const MatDesc* __restrict__ mats, const RItem* __restrict__ items,
+                 const float* __restrict__ Zin, float* __restrict__ Yout, float* __restrict__ G) {
+  constexpr int KT = WTraits<WT>::KT;
+  constexpr int TILE_BYTES = TM * KT * 2;
+  constexpr int ZS_BYTES = KT * 64;
+  __shared__ __align__(128) uint8_t smem[2 * TILE_BYTES + 2 * ZS_BYTES];
+  const uint32_t s_hi = smem_u32(smem), s_lo = s_hi + TILE_BYTES;
+  const uint32_t z_hi = s_lo + TILE_BYTES, z_lo = z_hi + ZS_BYTES;
+
+  const RItem it = items[blockIdx.x];
+  const MatDesc m = mats[it.b];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid >> 1, half = tid & 1;
+  const int nsteps = (m.K + KT - 1) / KT;
+  const float* z = Zin + static_cast<size_t>(m.zoff) * L;
+
+  // tall-skinny chunk [KT x 32]: thread -> row zr, 8 columns starting at zc*8 (two rounds for KT = 64)
+  const int zr = tid >> 2, zc = tid & 3;
+  constexpr int ZROUNDS = KT / 64 + (KT % 64 ? 1 : 0);   // 1 (KT = 32 uses half the threads) or 1 (64)
+  auto load_z = [&](int k0, float4 (&v)[2]) {
+    const int k = k0 + zr;
+    if (zr < KT && k < m.K) {
+      const float4* src = reinterpret_cast<const float4*>(z + static_cast<size_t>(k) * L + zc * 8);
+      v[0] = __ldg(src); v[1] = __ldg(src + 1);
+    } else {
+      v[0] = v[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  (void)ZROUNDS;
+
+  TileRegs<WT> regs;
+  float4 zv[2];
+  load_tile<WT>(regs, m, it.row0 + row, half * (KT / 2));
+  load_z(0, zv);
+
+  float acc[4][4] = {};
+  for (int step = 0; step < nsteps; ++step) {
+    __syncthreads();                                   // previous step's MMAs have read smem
+    store_tile<WT>(regs, s_hi, s_lo, row, half);
+    if (zr < KT) store_tall8(zv[0], zv[1], z_hi, z_lo, zr, zc);
+    __syncthreads();
+    if (step + 1 < nsteps) {
+      load_tile<WT>(regs, m, it.row0 + row, (step + 1) * KT + half * (KT / 2));
+      load_z((step + 1) * KT, zv);
+    }
+#pragma unroll
+    for (int ks = 0; ks < KT / 16; ++ks) {
+      uint32_t ah[4], al[4];
+      const uint32_t a_off = tile_off<KT>(warp * 16 + (lane & 15), ks * 2 + (lane >> 4));
+      ldsm_x4(s_hi + a_off, ah);
+      ldsm_x4(s_lo + a_off, al);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t bh[4], bl[4];
+        const uint32_t b_off = tile_off<32>(ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), np * 2 + (lane >> 4));
+        ldsm_x4_t(z_hi + b_off, bh);
+        ldsm_x4_t(z_lo + b_off, bl);
+        mma_bf16(acc[2 * np], ah, bh[0], bh[1]);
+        mma_bf16(acc[2 * np], al, bh[0], bh[1]);
+        mma_bf16(acc[2 * np], ah, bl[0], bl[1]);
+        mma_bf16(acc[2 * np + 1], ah, bh[2], bh[3]);
+        mma_bf16(acc[2 * np + 1], al, bh[2], bh[3]);
+        mma_bf16(acc[2 * np + 1], ah, bl[2], bl[3]);
+      }
+    }
+  }
+  // ---- output: c0,c1 = (row g, cols 2t,2t+1), c2,c3 = (row g+8, same cols) of each n8 tile
+  const int g = lane >> 2, t = lane & 3;
+  float* y = Yout + static_cast<size_t>(m.yoff) * L;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int r0 = it.row0 + warp * 16 + g, c = nt * 8 + 2 * t;
+    if (r0 < m.N) *reinterpret_cast<float2*>(y + static_cast<size_t>(r0) * L + c) = make_float2(acc[nt][0], acc[nt][1]);
+    if (r0 + 8 < m.N) *reinterpret_cast<float2*>(y + static_cast<size_t>(r0 + 8) * L + c) = make_float2(acc[nt][2], acc[nt][3]);
+  }
+  if (G != nullptr) {
+    // Gram of the tile through shared memory (rows beyond N are zero: they came from zero tiles)
+    __syncthreads();
+    float* ys = reinterpret_cast<float*>(smem);        // [128][33] fp32 = 16.9 KB <= tile bytes
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int r0 = warp * 16 + g, c = nt * 8 + 2 * t;
+      ys[r0 * 33 + c] = acc[nt][0]; ys[r0 * 33 + c + 1] = acc[nt][1];
+      ys[(r0 + 8) * 33 + c] = acc[nt][2]; ys[(r0 + 8) * 33 + c + 1] = acc[nt][3];
+    }
+    __syncthreads();
+    const int i = tid >> 3, j0 = (tid & 7) * 4;
+    float s[4] = {};
+#pragma unroll 8
+    for (int r = 0; r < TM; ++r) {
+      const float a = ys[r * 33 + i];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[q] += a * ys[r * 33 + j0 + q];
+    }
+    float* gdst = G + static_cast<size_t>(it.b) * L * L + i * L + j0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) atomicAdd(gdst + q, s[q]);
+  }
+}
+
+// ------------------------------------------------------------------------------------ Z += dW^T . Q
+// CTA = one KT-column block x row slab of one matrix; computes the [32 x KT] partial
+// (Q^T)[32 x n] . dW[n x KT] (A = Q^T through ldmatrix.trans of the [n][32] chunk, B = the weight
+// tile through ldmatrix.trans) and adds it into Z[k][col] with fp32 atomics (Z zeroed beforehand).
+// Warp w: m16 tile (w & 1) of the 32 Q-columns, n8 tiles [(w>>1)*NT, +NT) of the KT weight columns.
+template <typename WT>
+__global__ void __launch_bounds__(THREADS, 2)
+mul_left_kernel(const MatDesc* __restrict__ mats, const LItem* __restrict__ items,
+                const float* __restrict__ Qin, float* __restrict__ Zout) {
+  constexpr int KT = WTraits<WT>::KT;
+  constexpr int NT = KT / 32;                           // n8 tiles per warp: 2 (KT 64) or 1 (KT 32)
+  constexpr int TILE_BYTES = TM * KT * 2;
+  constexpr int QS_BYTES = TM * 64;
+  __shared__ __align__(128) uint8_t smem[2 * TILE_BYTES + 2 * QS_BYTES];
+  const uint32_t s_hi = smem_u32(smem), s_lo = s_hi + TILE_BYTES;
+  const uint32_t q_hi = s_lo + TILE_BYTES, q_lo = q_hi + QS_BYTES;
+
+  const LItem it = items[blockIdx.x];
+  const MatDesc m = mats[it.b];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = tid >> 1, half = tid & 1;
+  const int mt = warp & 1, ng = warp >> 1;
+  const float* qsrc = Qin + static_cast<size_t>(m.yoff) * L;
+  const int nsteps = (it.n1 - it.n0 + TM - 1) / TM;
+
+  // Q chunk [128 x 32]: thread -> row tid/2, 16 columns starting at (tid&1)*16 (2 chunks of 8)
+  auto load_q = [&](int n_base, float4 (&v)[4]) {
+    const int n = n_base + row;
+    if (n < it.n1) {
+      const float4* src = reinterpret_cast<const float4*>(qsrc + static_cast<size_t>(n) * L + half * 16);
+      v[0] = __ldg(src); v[1] = __ldg(src + 1); v[2] = __ldg(src + 2); v[3] = __ldg(src + 3);
+    } else {
+      v[0] = v[1] = v[2] = v[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  // rows beyond the slab are masked through Q (zero rows); the weight rows themselves are only
+  // guarded against the matrix end
+  TileRegs<WT> regs;
+  float4 qv[4];
+  load_tile<WT>(regs, m, it.n0 + row, it.k0 + half * (KT / 2));
+  load_q(it.n0, qv);
+
+  float acc[NT][4] = {};
+  for (int step = 0; step < nsteps; ++step) {
+    __syncthreads();
+    store_tile<WT>(regs, s_hi, s_lo, row, half);
+    store_tall8(qv[0], qv[1], q_hi, q_lo, row, half * 2);
+    store_tall8(qv[2], qv[3], q_hi, q_lo, row, half * 2 + 1);
+    __syncthreads();
+    if (step + 1 < nsteps) {
+      load_tile<WT>(regs, m, it.n0 + (step + 1) * TM + row, it.k0 + half * (KT / 2));
+      load_q(it.n0 + (step + 1) * TM, qv);
+    }
+#pragma unroll
+    for (int ks = 0; ks < TM / 16; ++ks) {
+      // A = Q^T: a0 (m 0-7, kk 0-7), a1 (m 8-15, kk 0-7), a2 (m 0-7, kk 8-15), a3 (m 8-15, kk 8-15);
+      // source 8x8 blocks are rows kk (n), 16-byte chunk = 8 Q-columns, transposed on load
+      uint32_t ah[4], al[4];
+      const uint32_t a_off = tile_off<32>(ks * 16 + (lane >> 4) * 8 + (lane & 7), mt * 2 + ((lane >> 3) & 1));
+      ldsm_x4_t(q_hi + a_off, ah);
+      ldsm_x4_t(q_lo + a_off, al);
+      if constexpr (NT == 2) {
+        uint32_t bh[4], bl[4];
+        const uint32_t b_off = tile_off<KT>(ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), ng * 2 + (lane >> 4));
+        ldsm_x4_t(s_hi + b_off, bh);
+        ldsm_x4_t(s_lo + b_off, bl);
+        mma_bf16(acc[0], ah, bh[0], bh[1]);
+        mma_bf16(acc[0], al, bh[0], bh[1]);
+        mma_bf16(acc[0], ah, bl[0], bl[1]);
+        mma_bf16(acc[1], ah, bh[2], bh[3]);
+        mma_bf16(acc[1], al, bh[2], bh[3]);
+        mma_bf16(acc[1], ah, bl[2], bl[3]);
+      } else {
+        uint32_t bh[2], bl[2];
+        const uint32_t b_off = tile_off<KT>(ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), ng);
+        ldsm_x2_t(s_hi + b_off, bh);
+        ldsm_x2_t(s_lo + b_off, bl);
+        mma_bf16(acc[0], ah, bh[0], bh[1]);
+        mma_bf16(acc[0], al, bh[0], bh[1]);
+        mma_bf16(acc[0], ah, bl[0], bl[1]);
+      }
+    }
+  }
+  // c0,c1 = (Q column mt*16+g, weight columns k0 + n8*8 + 2t, +1); c2,c3 = Q column +8
+  const int g = lane >> 2, t = lane & 3;
+  float* zdst = Zout + static_cast<size_t>(m.zoff) * L;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int k = it.k0 + (ng * NT + j) * 8 + 2 * t;
+    const int c = mt * 16 + g;
+    if (k < m.K) {
+      atomicAdd(zdst + static_cast<size_t>(k) * L + c, acc[j][0]);
+      atomicAdd(zdst + static_cast<size_t>(k) * L + c + 8, acc[j][2]);
+    }
+    if (k + 1 < m.K) {
+      atomicAdd(zdst + static_cast<size_t>(k + 1) * L + c, acc[j][1]);
+      atomicAdd(zdst + static_cast<size_t>(k + 1) * L + c + 8, acc[j][3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ probes
+// Rademacher (+-1) probes: as good a test matrix as Gaussians for the range finder (sub-Gaussian),
+// one hash per 32 entries.
+__global__ void probes_kernel(float* __restrict__ Z, long long rows, unsigned long long seed) {
+  const long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (r >= rows) return;
+  unsigned long long z = seed + static_cast<unsigned long long>(r) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const uint32_t bits = static_cast<uint32_t>(z >> 16);
+  float4* dst = reinterpret_cast<float4*>(Z + r * L);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    dst[i] = make_float4((bits >> (4 * i)) & 1 ? 1.f : -1.f, (bits >> (4 * i + 1)) & 1 ? 1.f : -1.f,
+                         (bits >> (4 * i + 2)) & 1 ? 1.f : -1.f, (bits >> (4 * i + 3)) & 1 ? 1.f : -1.f);
+}
+
+// ------------------------------------------------------------------------------------ tall transform
+// out_row = in_row . M with M = V diag(1/s) (null directions, s_j <= 1e-6 s_0, dropped), in place
+// allowed; optional Gram of the OUTPUT rows (mode bit 1) -- or Gram only, no multiply (mode bit 0
+// clear). space: 0 = rows indexed through yoff / N, 1 = through zoff / K.
+__global__ void __launch_bounds__(THREADS)
+tall_transform_kernel(const MatDesc* __restrict__ mats, const TItem* __restrict__ items, int space,
+                      float* __restrict__ buf, const float* __restrict__ V, const float* __restrict__ sig,
+                      int do_mul, float* __restrict__ G) {
+  __shared__ float Ms[L][L + 1];
+  __shared__ float rows_s[THREADS][L + 1];
+  const TItem it = items[blockIdx.x];
+  const MatDesc m = mats[it.b];
+  const int rows = space ? m.K : m.N;
+  float* base = buf + static_cast<size_t>(space ? m.zoff : m.yoff) * L;
+  const int tid = threadIdx.x;
+  if (do_mul) {
+    const float* v = V + static_cast<size_t>(it.b) * L * L;
+    const float* s = sig + static_cast<size_t>(it.b) * L;
+    const float smax = s[0];
+    for (int i = tid; i < L * L; i += THREADS) {
+      const int r = i >> 5, c = i & 31;
+      const float sc = s[c];
+      Ms[r][c] = (sc > 1e-6f * smax && sc > 0.f) ? v[i] / sc : 0.f;
+    }
+  }
+  __syncthreads();
+  const int row = it.row0 + tid;
+  float x[L];
+  if (row < rows) {
+    const float4* src = reinterpret_cast<const float4*>(base + static_cast<size_t>(row) * L);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 a = src[i];
+      x[4 * i] = a.x; x[4 * i + 1] = a.y; x[4 * i + 2] = a.z; x[4 * i + 3] = a.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < L; ++i) x[i] = 0.f;
+  }
+  if (do_mul) {
+    float o[L];
+#pragma unroll
+    for (int j = 0; j < L; ++j) o[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      const float xi = x[i];
+#pragma unroll
+      for (int j = 0; j < L; ++j) o[j] += xi * Ms[i][j];
+    }
+#pragma unroll
+    for (int j = 0; j < L; ++j) x[j] = o[j];
+    if (row < rows) {
+      float4* dst = reinterpret_cast<float4*>(base + static_cast<size_t>(row) * L);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+    }
+  }
+  if (G != nullptr) {
+#pragma unroll
+    for (int j = 0; j < L; ++j) rows_s[tid][j] = x[j];
+    __syncthreads();
+    const int i = tid >> 3, j0 = (tid & 7) * 4;
+    float s4[4] = {};
+#pragma unroll 8
+    for (int r = 0; r < THREADS; ++r) {
+      const float a = rows_s[r][i];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s4[q] += a * rows_s[r][j0 + q];
+    }
+    float* gdst = G + static_cast<size_t>(it.b) * L * L + i * L + j0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) atomicAdd(gdst + q, s4[q]);
+  }
+}
+
+// ------------------------------------------------------------------------------------ Jacobi
+// One CTA (256 threads) per symmetric 32x32 matrix: cyclic Jacobi, round-robin ordering; the 16
+// disjoint rotations of a step are applied in parallel: thread = (rotation k = tid/16, index
+// tid%16 and +16). Outputs eigenvectors (columns, descending eigenvalue) and sqrt(max(eig, 0)).
+__global__ void __launch_bounds__(256)
+jacobi32_kernel(const float* __restrict__ G, float* __restrict__ V, float* __restrict__ sigma, int sweeps) {
+  __shared__ float A[L][L + 1];
+  __shared__ float Q[L][L + 1];
+  __shared__ int perm[L];
+  __shared__ float cs[16], sn[16];
+  __shared__ int pp[16], qq[16];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* g = G + static_cast<size_t>(b) * L * L;
+  for (int i = tid; i < L * L; i += 256) {
+    A[i >> 5][i & 31] = g[i];
+    Q[i >> 5][i & 31] = ((i >> 5) == (i & 31)) ? 1.f : 0.f;
+  }
+  if (tid < L) perm[tid] = tid;
+  __syncthreads();
+  const int k = tid >> 4, idx = tid & 15;
+  for (int sw = 0; sw < sweeps; ++sw) {
+    for (int step = 0; step < L - 1; ++step) {
+      if (tid < 16) {
+        int p = perm[tid], q = perm[L - 1 - tid];
+        if (p > q) { const int tmp = p; p = q; q = tmp; }
+        const float apq = A[p][q], app = A[p][p], aqq = A[q][q];
+        float c = 1.f, s = 0.f;
+        if (fabsf(apq) > 1e-30f) {
+          const float tau = (aqq - app) / (2.f * apq);
+          const float tt = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+          c = rsqrtf(1.f + tt * tt);
+          s = tt * c;
+        }
+        cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
+      }
+      __syncthreads();
+      {
+        const int p = pp[k], q = qq[k];
+        const float c = cs[k], s = sn[k];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {          // columns p, q of A and of the eigenvector matrix
+          const int r = idx + 16 * h;
+          const float aip = A[r][p], aiq = A[r][q];
+          A[r][p] = c * aip - s * aiq;
+          A[r][q] = s * aip + c * aiq;
+          const float vip = Q[r][p], viq = Q[r][q];
+          Q[r][p] = c * vip - s * viq;
+          Q[r][q] = s * vip + c * viq;
+        }
+      }
+      __syncthreads();
+      {
+        const int p = pp[k], q = qq[k];
+        const float c = cs[k], s = sn[k];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {          // rows p, q of A
+          const int col = idx + 16 * h;
+          const float apj = A[p][col], aqj = A[q][col];
+          A[p][col] = c * apj - s * aqj;
+          A[q][col] = s * apj + c * aqj;
+        }
+      }
+      int nxt = 0;
+      if (tid < L) nxt = (tid >= 1) ? perm[tid == 1 ? L - 1 : tid - 1] : perm[0];
+      __syncthreads();
+      if (tid < L) perm[tid] = nxt;
+      __syncthreads();
+    }
+  }
+  if (tid < L) {
+    const float w = A[tid][tid];
+    int rank = 0;
+    for (int j = 0; j < L; ++j) {
+      const float wj = A[j][j];
+      rank += (wj > w) || (wj == w && j < tid);
+    }
+    sigma[static_cast<size_t>(b) * L + rank] = sqrtf(fmaxf(w, 0.f));
+    float* v = V + static_cast<size_t>(b) * L * L;
+    for (int i = 0; i < L; ++i) v[i * L + rank] = Q[i][tid];
+  }
+}
+
+// ------------------------------------------------------------------------------------ factors
+// up[n, j]   = s_j * sum_i Q[n, i] Uh[i, j]                      (space 0, rows = N)   -> out[n*r + j]
+// down[j, k] = (1/s_j) * sum_i Bt[k, i] Uh[i, j]  (0 if null)    (space 1, rows = K)   -> out[N*r + j*K + k]
+__global__ void __launch_bounds__(THREADS)
+factors_kernel(const MatDesc* __restrict__ mats, const TItem* __restrict__ items, int space,
+               const float* __restrict__ buf, const float* __restrict__ V, const float* __restrict__ sig,
+               int r, float* __restrict__ out) {
+  __shared__ float Ms[L][17];
+  const TItem it = items[blockIdx.x];
+  const MatDesc m = mats[it.b];
+  const int rows = space ? m.K : m.N;
+  const float* base = buf + static_cast<size_t>(space ? m.zoff : m.yoff) * L;
+  const float* v = V + static_cast<size_t>(it.b) * L * L;
+  const float* s = sig + static_cast<size_t>(it.b) * L;
+  const int tid = threadIdx.x;
+  const float smax = s[0];
+  for (int i = tid; i < L * 16; i += THREADS) {
+    const int rr = i >> 4, c = i & 15;
+    float val = 0.f;
+    if (c < r) {
+      const float sc = s[c];
+      val = space ? ((sc > 1e-6f * smax && sc > 0.f) ? v[rr * L + c] / sc : 0.f) : v[rr * L + c] * sc;
+    }
+    Ms[rr][c] = val;
+  }
+  __syncthreads();
+  const int row = it.row0 + tid;
+  if (row >= rows) return;
+  float x[L];
+  const float4* src = reinterpret_cast<const float4*>(base + static_cast<size_t>(row) * L);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 a = src[i];
+    x[4 * i] = a.x; x[4 * i + 1] = a.y; x[4 * i + 2] = a.z; x[4 * i + 3] = a.w;
+  }
+  float* o = out + m.out_off;
+  for (int j = 0; j < r; ++j) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < L; ++i) acc += x[i] * Ms[i][j];
+    if (space) o[static_cast<size_t>(m.N) * r + static_cast<size_t>(j) * m.K + row] = acc;
+    else o[static_cast<size_t>(row) * r + j] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------ quantile clamp
+// cli_svd.py:43-47: hi = torch.quantile(cat(U.flatten(), Vh.flatten()), q); clamp both to [-hi, hi].
+// torch.quantile ("linear"): pos = q (n-1) evaluated in fp32, v = sorted[floor pos].lerp(sorted[ceil pos],
+// frac). The two order statistics are found EXACTLY by a 4 x 8-bit radix select on the
+// order-preserving integer image of the floats (one CTA per matrix, data is L2-resident).
+__device__ __forceinline__ uint32_t fkey(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__global__ void __launch_bounds__(1024)
+quantile_clamp_kernel(const MatDesc* __restrict__ mats, int r, float q, float* __restrict__ out,
+                      float* __restrict__ hi_out) {
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned int sel_prefix, sel_rank, s_min_above, s_count_le;
+  const MatDesc m = mats[blockIdx.x];
+  float* x = out + m.out_off;
+  const long long n = static_cast<long long>(r) * (static_cast<long long>(m.N) + m.K);
+  const int tid = threadIdx.x;
+  const float pos = q * static_cast<float>(n - 1);
+  const long long k_lo = static_cast<long long>(floorf(pos));
+  const long long k_hi = static_cast<long long>(ceilf(pos));
+  const float w = pos - floorf(pos);
+  // ---- k_lo-th smallest (0-based)
+  uint32_t prefix = 0, mask = 0;
+  unsigned int rank = static_cast<unsigned int>(k_lo);
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = tid; i < 256; i += 1024) hist[i] = 0;
+    __syncthreads();
+    for (long long i = tid; i < n; i += 1024) {
+      const uint32_t key = fkey(x[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      unsigned int cum = 0, b = 0;
+      for (; b < 256; ++b) {
+        if (cum + hist[b] > rank) break;
+        cum += hist[b];
+      }
+      sel_prefix = prefix | (static_cast<uint32_t>(b) << shift);
+      sel_rank = rank - cum;
+    }
+    __syncthreads();
+    prefix = sel_prefix;
+    rank = sel_rank;
+    mask |= 0xffu << shift;
+    __syncthreads();
+  }
+  const float v_lo = fkey_inv(prefix);
+  // ---- the next order statistic: equal to v_lo if it has duplicates past k_lo, else the
+  // smallest element above it
+  if (tid == 0) { s_min_above = 0xffffffffu; s_count_le = 0; }
+  __syncthreads();
+  unsigned int cnt = 0, mn = 0xffffffffu;
+  for (long long i = tid; i < n; i += 1024) {
+    const uint32_t key = fkey(x[i]);
+    cnt += key <= prefix;
+    if (key > prefix) mn = min(mn, key);
+  }
+  atomicAdd(&s_count_le, cnt);
+  atomicMin(&s_min_above, mn);
+  __syncthreads();
+  float v_hi = v_lo;
+  if (k_hi > k_lo && static_cast<long long>(s_count_le) <= k_hi && s_min_above != 0xffffffffu)
+    v_hi = fkey_inv(s_min_above);
+  // torch.lerp
+  const float d = v_hi - v_lo;
+  const float hi = (w < 0.5f) ? v_lo + w * d : v_hi - d * (1.f - w);
+  if (tid == 0 && hi_out) hi_out[blockIdx.x] = hi;
+  for (long long i = tid; i < n; i += 1024) x[i] = fminf(fmaxf(x[i], -hi), hi);
+}
+
+// ------------------------------------------------------------------------------------ host side
+struct Plan {
+  std::vector<MatDesc> mats;
+  std::vector<RItem> ritems;
+  std::vector<LItem> litems;
+  std::vector<TItem> ty, tz;
+  long long sumN = 0, sumK = 0, out_elems = 0;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static void make_plan(Plan& p, const void* const* Wt, const void* const* Wb, const int* N, const int* K,
+                      int batch, int rank, int kt) {
+  p.mats.resize(batch);
+  for (int b = 0; b < batch; ++b) {
+    MatDesc& m = p.mats[b];
+    m.wt = Wt[b]; m.wb = Wb ? Wb[b] : nullptr; m.N = N[b]; m.K = K[b];
+    m.yoff = p.sumN; m.zoff = p.sumK; m.out_off = p.out_elems;
+    p.sumN += N[b]; p.sumK += K[b];
+    p.out_elems += static_cast<long long>(rank) * (static_cast<long long>(N[b]) + K[b]);
+    for (int r0 = 0; r0 < N[b]; r0 += TM) p.ritems.push_back({b, r0});
+    // row slabs of <= 1024 rows: bounds the serial length of one CTA (per-SM ingest ~100 GB/s)
+    const int slabs = (N[b] + 1023) / 1024;
+    const int per = ((N[b] + slabs - 1) / slabs + TM - 1) / TM * TM;
+    for (int k0 = 0; k0 < K[b]; k0 += kt)
+      for (int n0 = 0; n0 < N[b]; n0 += per) p.litems.push_back({b, k0, n0, n0 + per < N[b] ? n0 + per : N[b]});
+    for (int r0 = 0; r0 < N[b]; r0 += THREADS) p.ty.push_back({b, r0});
+    for (int r0 = 0; r0 < K[b]; r0 += THREADS) p.tz.push_back({b, r0});
+  }
+}
+
+struct Layout {
+  size_t mats, ritems, litems, ty, tz, Y, Z, G, V, sig, total;
+};
+static Layout make_layout(const Plan& p, int batch) {
+  Layout l;
+  size_t o = 0;
+  l.mats = o; o = align_up(o + p.mats.size() * sizeof(MatDesc), 256);
+  l.ritems = o; o = align_up(o + p.ritems.size() * sizeof(RItem), 256);
+  l.litems = o; o = align_up(o + p.litems.size() * sizeof(LItem), 256);
+  l.ty = o; o = align_up(o + p.ty.size() * sizeof(TItem), 256);
+  l.tz = o; o = align_up(o + p.tz.size() * sizeof(TItem), 256);
+  l.Y = o; o = align_up(o + static_cast<size_t>(p.sumN) * L * 4, 256);
+  l.Z = o; o = align_up(o + static_cast<size_t>(p.sumK) * L * 4, 256);
+  l.G = o; o = align_up(o + static_cast<size_t>(batch) * L * L * 4, 256);
+  l.V = o; o = align_up(o + static_cast<size_t>(batch) * L * L * 4, 256);
+  l.sig = o; o = align_up(o + static_cast<size_t>(batch) * L * 4, 256);
+  l.total = o;
+  return l;
+}
+
+}  // namespace lbsvd2
+
+using namespace lbsvd2;
+
+static inline int kt_of(int w_dtype) { return w_dtype == LB_F32 ? 32 : 64; }
+
+extern "C" long long lb_svd_workspace_bytes(const int* N, const int* K, int batch, int w_dtype) {
+  if (batch <= 0 || N == nullptr || K == nullptr) return LB_ERR_SHAPE;
+  Plan p;
+  std::vector<const void*> dummy(batch, nullptr);
+  make_plan(p, dummy.data(), nullptr, N, K, batch, 16, kt_of(w_dtype));
+  return static_cast<long long>(make_layout(p, batch).total);
+}
+
+#define LB_SVD_CHECK() do { if (cudaGetLastError() != cudaSuccess) return LB_ERR_CUDA; } while (0)
+
+extern "C" int lb_svd_truncated_batched(const void* const* Wt, const void* const* Wb, const int* N,
+                                        const int* K, int batch, int w_dtype, int rank, int power_iters,
+                                        float clamp_q, unsigned long long seed, float* out,
+                                        float* sigma_out, float* hi_out, void* workspace,
+                                        long long workspace_bytes, void* stream) {
+  if (batch <= 0 || Wt == nullptr || N == nullptr || K == nullptr || out == nullptr || workspace == nullptr)
+    return LB_ERR_SHAPE;
+  if (rank < 1 || rank > 16) return LB_ERR_RANK;
+  if (w_dtype != LB_F32 && w_dtype != LB_BF16 && w_dtype != LB_F16) return LB_ERR_DTYPE;
+  if (power_iters < 0 || power_iters > 8) return LB_ERR_SHAPE;
+  const int vec = w_dtype == LB_F32 ? 4 : 8;
+  for (int b = 0; b < batch; ++b) {
+    if (N[b] <= 0 || K[b] <= 0 || (K[b] % vec) != 0) return LB_ERR_SHAPE;   // 16-byte row pitch
+    if ((reinterpret_cast<uintptr_t>(Wt[b]) | reinterpret_cast<uintptr_t>(Wb ? Wb[b] : nullptr)) & 15) return LB_ERR_ALIGN;
+  }
+  const int kt = kt_of(w_dtype);
+  Plan p;
+  make_plan(p, Wt, Wb, N, K, batch, rank, kt);
+  const Layout lay = make_layout(p, batch);
+  if (static_cast<long long>(lay.total) > workspace_bytes) return LB_ERR_SHAPE;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  // tables: pageable host -> device (the runtime stages pageable sources before returning)
+  if (cudaMemcpyAsync(ws + lay.mats, p.mats.data(), p.mats.size() * sizeof(MatDesc), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(ws + lay.ritems, p.ritems.data(), p.ritems.size() * sizeof(RItem), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(ws + lay.litems, p.litems.data(), p.litems.size() * sizeof(LItem), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(ws + lay.ty, p.ty.data(), p.ty.size() * sizeof(TItem), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+      cudaMemcpyAsync(ws + lay.tz, p.tz.data(), p.tz.size() * sizeof(TItem), cudaMemcpyHostToDevice, st) != cudaSuccess)
+    return LB_ERR_CUDA;
+  const MatDesc* mats = reinterpret_cast<const MatDesc*>(ws + lay.mats);
+  const RItem* ritems = reinterpret_cast<const RItem*>(ws + lay.ritems);
+  const LItem* litems = reinterpret_cast<const LItem*>(ws + lay.litems);
+  const TItem* ty = reinterpret_cast<const TItem*>(ws + lay.ty);
+  const TItem* tz = reinterpret_cast<const TItem*>(ws + lay.tz);
+  float* Y = reinterpret_cast<float*>(ws + lay.Y);
+  float* Z = reinterpret_cast<float*>(ws + lay.Z);
+  float* G = reinterpret_cast<float*>(ws + lay.G);
+  float* V = reinterpret_cast<float*>(ws + lay.V);
+  float* sig = sigma_out ? sigma_out : reinterpret_cast<float*>(ws + lay.sig);
+  const size_t g_bytes = static_cast<size_t>(batch) * L * L * 4;
+  const int nR = static_cast<int>(p.ritems.size()), nL = static_cast<int>(p.litems.size());
+  const int nTy = static_cast<int>(p.ty.size()), nTz = static_cast<int>(p.tz.size());
+
+  auto mul_right = [&](bool gram) -> bool {
+    if (gram && cudaMemsetAsync(G, 0, g_bytes, st) != cudaSuccess) return false;
+    float* g = gram ? G : nullptr;
+    if (w_dtype == LB_F16) mul_right_kernel<__half><<<nR, THREADS, 0, st>>>(mats, ritems, Z, Y, g);
+    else if (w_dtype == LB_BF16) mul_right_kernel<__nv_bfloat16><<<nR, THREADS, 0, st>>>(mats, ritems, Z, Y, g);
+    else mul_right_kernel<float><<<nR, THREADS, 0, st>>>(mats, ritems, Z, Y, g);
+    return cudaGetLastError() == cudaSuccess;
+  };
+  auto mul_left = [&]() -> bool {
+    if (cudaMemsetAsync(Z, 0, static_cast<size_t>(p.sumK) * L * 4, st) != cudaSuccess) return false;
+    if (w_dtype == LB_F16) mul_left_kernel<__half><<<nL, THREADS, 0, st>>>(mats, litems, Y, Z);
+    else if (w_dtype == LB_BF16) mul_left_kernel<__nv_bfloat16><<<nL, THREADS, 0, st>>>(mats, litems, Y, Z);
+    else mul_left_kernel<float><<<nL, THREADS, 0, st>>>(mats, litems, Y, Z);
+    return cudaGetLastError() == cudaSuccess;
+  };
+  // orth(buf): [Gram given in G] -> Jacobi -> buf <- buf V diag(1/s) (+ Gram of the result)
+  auto jacobi = [&](int sweeps) -> bool {
+    jacobi32_kernel<<<batch, 256, 0, st>>>(G, V, sig, sweeps);
+    return cudaGetLastError() == cudaSuccess;
+  };
+  auto transform = [&](int space, bool mul, bool gram) -> bool {
+    if (gram && cudaMemsetAsync(G, 0, g_bytes, st) != cudaSuccess) return false;
+    tall_transform_kernel<<<space ? nTz : nTy, THREADS, 0, st>>>(mats, space ? tz : ty, space, space ? Z : Y, V, sig,
+                                                               mul ? 1 : 0, gram ? G : nullptr);
+    return cudaGetLastError() == cudaSuccess;
+  };
+
+  probes_kernel<<<static_cast<int>((p.sumK + 255) / 256), 256, 0, st>>>(Z, p.sumK, seed);
+  LB_SVD_CHECK();
+  if (!mul_right(true)) return LB_ERR_CUDA;                       // Y = dW Om, G = Y^T Y
+  for (int it = 0; it < power_iters; ++it) {
+    if (!jacobi(6) || !transform(0, true, false)) return LB_ERR_CUDA;    // Y <- orth(Y)
+    if (!mul_left()) return LB_ERR_CUDA;                                   // Z = dW^T Y
+    if (!transform(1, false, true) || !jacobi(6) || !transform(1, true, false)) return LB_ERR_CUDA;   // Z <- orth(Z)
+    if (!mul_right(true)) return LB_ERR_CUDA;                              // Y = dW Z, G
+  }
+  // Q = orth2(Y): the basis the projected problem is solved in must be orthonormal to fp32 accuracy
+  if (!jacobi(6) || !transform(0, true, true) || !jacobi(6) || !transform(0, true, false)) return LB_ERR_CUDA;
+  if (!mul_left()) return LB_ERR_CUDA;                                     // B^T = dW^T Q
+  if (!transform(1, false, true) || !jacobi(10)) return LB_ERR_CUDA;       // B B^T = Uh diag(s^2) Uh^T
+  factors_kernel<<<nTy, THREADS, 0, st>>>(mats, ty, 0, Y, V, sig, rank, out);
+  LB_SVD_CHECK();
+  factors_kernel<<<nTz, THREADS, 0, st>>>(mats, tz, 1, Z, V, sig, rank, out);
+  LB_SVD_CHECK();
+  if (clamp_q > 0.f) {
+    quantile_clamp_kernel<<<batch, 1024, 0, st>>>(mats, rank, clamp_q, out, hi_out);
+    LB_SVD_CHECK();
+  }
+  return LB_OK;
+}

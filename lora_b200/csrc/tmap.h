@@ -72,6 +72,55 @@ inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, dim3 block, size
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// Benchmark knob: LB_NO_SPLITK=1 in the environment disables the automatic split-K plans.
+inline bool splitk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LB_NO_SPLITK");
+    v = (e != nullptr && e[0] == '1') ? 0 : 1;
+  }
+  return v != 0;
+}
+
+// Split-K workspace (fused_core.cuh, SPLITK): one allocation per device, handed out as a ring so
+// that consecutive launches never share a region (a launch is stream-ordered after the previous
+// user of its region as long as fewer than ~4 launches run concurrently). Allocated at the first
+// split-K launch -- which must not happen inside a stream capture (cudaMalloc is illegal there);
+// the training engine's warm-up steps precede its capture.
+struct SplitWorkspace {
+  float* buf = nullptr;
+  unsigned int* counters = nullptr;
+  size_t bytes = 0, off = 0;
+  unsigned int n_counters = 0, counter_off = 0;
+};
+inline bool split_ws_reserve(cudaStream_t stream, size_t need_bytes, unsigned int need_counters,
+                             float** ws, unsigned int** counters) {
+  static SplitWorkspace per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return false;
+  SplitWorkspace& w = per_dev[dev];
+  if (w.buf == nullptr) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return false;
+    const size_t bytes = size_t(96) << 20;
+    const unsigned int n = 1u << 16;
+    if (cudaMalloc(&w.buf, bytes) != cudaSuccess) return false;
+    if (cudaMalloc(&w.counters, n * sizeof(unsigned int)) != cudaSuccess) return false;
+    if (cudaMemset(w.counters, 0, n * sizeof(unsigned int)) != cudaSuccess) return false;
+    w.bytes = bytes;
+    w.n_counters = n;
+  }
+  need_bytes = (need_bytes + 255) & ~size_t(255);
+  if (need_bytes > w.bytes / 2 || need_counters > w.n_counters / 2) return false;
+  if (w.off + need_bytes > w.bytes) w.off = 0;
+  if (w.counter_off + need_counters > w.n_counters) w.counter_off = 0;
+  *ws = reinterpret_cast<float*>(reinterpret_cast<char*>(w.buf) + w.off);
+  *counters = w.counters + w.counter_off;
+  w.off += need_bytes;
+  w.counter_off += need_counters;
+  return true;
+}
+
 inline EncodeTiledFn encode_tiled_fn() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;

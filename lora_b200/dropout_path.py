@@ -4,13 +4,15 @@ state of every operator built by inject_trainable_lora_extended and by the monke
 
     y = base(x) + mask o (up(sel(down(x)))) / (1-p) * scale            (lora.py:53-58, 130-135)
 
-The mask sits between the up-projection and the sum, so the branch cannot be folded into the base
-accumulator. The fused kernel still produces base(x) and T = down(x) in one pass over x; the masked
-rank-r update is one extra elementwise pass over Y (lb_lora_up_dropout). Backward recomputes the
-same counter-based mask: dT = (mask o gY) . B (lb_lora_dropout_dt) is handed to the fused dX kernel
-as T_in, dB uses the masked reduction (lb_lora_wgrad_masked).
+The mask sits between the up-projection and the sum, so the branch cannot be accumulated into the
+base accumulator -- but it still never leaves the SM: the fused kernel gives the LoRA product
+T'.U^T its own TMEM columns and applies keep(m,n)/(1-p) while the tile is drained
+(lb_lora_linear_fwd_dropout / lb_lora_conv2d_fwd_dropout; csrc/fused_core.cuh, DROP): ONE launch,
+no extra pass over Y. Backward recomputes the same counter-based mask: dT = (mask o gY) . B
+(lb_lora_dropout_dt) is handed to the fused dX kernel as T_in, dB uses the masked reduction
+(lb_lora_wgrad_masked / lb_lora_wgrad_pair).
 
-The keep-mask is a hash of (per-call device seed, element index) -- NOT ATen's Philox stream, so
+The keep-mask is a hash of (per-call device seed, element index; csrc/dropmask.cuh) -- NOT ATen's Philox stream, so
 parity with the reference under dropout is distributional (keep probability, 1/(1-p) scaling,
 forward/backward mask consistency; tests/test_dropout_gpu.py), not bitwise.
 """
@@ -46,8 +48,8 @@ class _LoraLinearDropoutFn(torch.autograd.Function):
         diag = mod._selector_diag()
         scale, p = float(mod.scale), float(mod.dropout.p)
         seed = _fresh_seed(x.device)
-        y, T = ops.fused_linear(x2d, w16, b32, down16, B32, r, 1, diag, 0.0, r, odt, True)
-        ops.up_dropout_(y, T, B32, r, 1, diag, scale, p, seed, r)
+        y, T = ops.fused_linear(x2d, w16, b32, down16, B32, r, 1, diag, scale, r, odt, True,
+                                drop_p=p, seed=seed)
         ctx.mod, ctx.cdt, ctx.scale, ctx.p, ctx.diag = mod, cdt, scale, p, diag
         ctx.x_shape, ctx.x_dtype = x.shape, x.dtype
         ctx.save_for_backward(x2d, T, A, B, seed)
@@ -117,11 +119,8 @@ class _LoraConv2dDropoutFn(torch.autograd.Function):
         scale, p = float(mod.scale), float(mod.dropout.p)
         seed = _fresh_seed(x.device)
         cout = conv.out_channels
-        y, T = ops.fused_conv2d(x16, w_f, b32, down16, B32, 0, r, 1, 0, diag, 0.0, r, cout, kh, kw,
-                                ph, pw, False, odt, True)
-        n, _, h, w = y.shape
-        y2d = y.permute(0, 2, 3, 1).reshape(n * h * w, cout)      # NHWC bytes viewed as [P, Cout]
-        ops.up_dropout_(y2d, T, B32, r, 1, diag, scale, p, seed, r)
+        y, T = ops.fused_conv2d(x16, w_f, b32, down16, B32, 0, r, 1, 0, diag, scale, r, cout, kh, kw,
+                                ph, pw, False, odt, True, drop_p=p, seed=seed)
         ctx.mod, ctx.cdt, ctx.scale, ctx.p, ctx.diag = mod, cdt, scale, p, diag
         ctx.geom, ctx.x_dtype = (kh, kw, ph, pw), x.dtype
         ctx.save_for_backward(x16, T, A, B, seed)

@@ -80,10 +80,12 @@ def cast_weight(w: torch.Tensor, dtype, want_plain: bool, want_t: bool):
 def fused_linear(x2d: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tensor],
                  down16: torch.Tensor, up: torch.Tensor, up_rs: int, up_cs: int,
                  diag: Optional[torch.Tensor], scale: float, r: int, out_dtype,
-                 want_t: bool, t_in: Optional[torch.Tensor] = None
+                 want_t: bool, t_in: Optional[torch.Tensor] = None, drop_p: float = 0.0,
+                 seed: Optional[torch.Tensor] = None
                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """Y = x2d.w16^T + bias + ((x2d.down16^T) * scale*diag) . up^T ; returns (Y, T or None).
-    t_in: use these rank-r activations [M,16] instead of x2d.down16^T (dropout backward)."""
+    t_in: use these rank-r activations [M,16] instead of x2d.down16^T (dropout backward).
+    drop_p > 0 (+ seed: int64[1] on the device): nn.Dropout on the branch, masked in the drain."""
     _req_cuda(x2d, w16, down16, up)
     M, K = x2d.shape
     N = w16.shape[0]
@@ -91,6 +93,15 @@ def fused_linear(x2d: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tens
     assert x2d.is_contiguous() and w16.is_contiguous() and down16.is_contiguous()
     y = torch.empty((M, N), device=x2d.device, dtype=out_dtype)
     t = torch.empty((M, R_PAD), device=x2d.device, dtype=torch.float32) if want_t else None
+    if drop_p > 0.0:
+        assert t_in is None and seed is not None and seed.dtype == torch.int64 and seed.is_cuda
+        check(_C.lib.lb_lora_linear_fwd_dropout(ptr(x2d), ptr(w16), ptr(bias), ptr(down16), ptr(up),
+                                                up_rs, up_cs, ptr(diag), float(scale), ptr(y), ptr(t),
+                                                M, K, N, r, dtype_code(x2d.dtype), dtype_code(out_dtype),
+                                                float(drop_p), ptr(seed), stream_ptr()),
+              "lb_lora_linear_fwd_dropout")
+        _count()
+        return y, t
     check(_C.lib.lb_lora_linear_fwd(ptr(x2d), ptr(w16), ptr(bias), ptr(down16), ptr(up),
                                     up_rs, up_cs, ptr(diag), float(scale), ptr(y), ptr(t), ptr(t_in),
                                     M, K, N, r, dtype_code(x2d.dtype), dtype_code(out_dtype),
@@ -154,7 +165,8 @@ def fused_conv2d(x_nhwc: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.T
                  down16: torch.Tensor, up: torch.Tensor, up_off: int, up_rs: int, up_cs: int,
                  up_gs: int, diag: Optional[torch.Tensor], scale: float, r: int, cout: int,
                  kh: int, kw: int, pad_h: int, pad_w: int, per_tap: bool, out_dtype,
-                 want_t: bool, t_in: Optional[torch.Tensor] = None
+                 want_t: bool, t_in: Optional[torch.Tensor] = None, drop_p: float = 0.0,
+                 seed: Optional[torch.Tensor] = None
                  ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """x_nhwc: a [N,C,H,W] tensor in channels_last memory format (NHWC bytes). Returns
     (Y as [N,cout,H,W] channels_last, T [N*H*W,16] or None)."""
@@ -166,6 +178,15 @@ def fused_conv2d(x_nhwc: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.T
     t = torch.empty((n * h * w, R_PAD), device=x_nhwc.device, dtype=torch.float32) if want_t else None
     import ctypes
     up_ptr = ctypes.c_void_p(up.data_ptr() + 4 * up_off)
+    if drop_p > 0.0:     # forward with nn.Dropout on the branch: masked in the drain, one launch
+        assert t_in is None and not per_tap and up_gs == 0 and seed is not None and seed.dtype == torch.int64
+        check(_C.lib.lb_lora_conv2d_fwd_dropout(ptr(x_nhwc), ptr(w16), ptr(bias), ptr(down16), up_ptr, up_rs,
+                                                up_cs, ptr(diag), float(scale), ptr(y), ptr(t), n, h, w,
+                                                cin, cout, kh, kw, pad_h, pad_w, r, dtype_code(x_nhwc.dtype),
+                                                dtype_code(out_dtype), float(drop_p), ptr(seed), stream_ptr()),
+              "lb_lora_conv2d_fwd_dropout")
+        _count()
+        return y, t
     check(_C.lib.lb_lora_conv2d_fwd(ptr(x_nhwc), ptr(w16), ptr(bias), ptr(down16), up_ptr, up_rs,
                                     up_cs, up_gs, ptr(diag), float(scale), ptr(y), ptr(t), ptr(t_in),
                                     n, h, w,

@@ -5,10 +5,12 @@ per LoRA site, dW = (W_tuned - W_base) (conv: flattened to [Cout, Cin*kh*kw]), k
 singular triplets, up = U_r diag(S_r), down = Vh_r, clamp both symmetrically at the
 `clamp_quantile` quantile of their joint values, write them into lora_up / lora_down.
 
-The reference loops over sites calling a full `torch.linalg.svd`. Here all same-shape sites are
-processed together by the primitives in csrc/svd.cu (randomized range finder, 32 probes,
-q power iterations re-orthonormalised through a 32x32 Jacobi eigen-solve): the only passes over the weights are
-2(q+1) streaming reads of (W_tuned, W_base).
+The reference loops over sites calling a full `torch.linalg.svd`. Here ALL sites of a model,
+whatever their shapes, go through ONE C call (csrc/svd_batched.cu: lb_svd_truncated_batched --
+randomized range finder, 32 probes, q power iterations re-orthonormalised through a 32x32 Jacobi
+eigen-solve, exact quantile clamp): the only passes over the weights are 2(q+1) streaming reads of
+(W_tuned, W_base), q = 1 by default (4 passes), with the contraction on the tensor cores
+(3-term split-bf16, fp32-faithful).
 
 Singular vectors are unique up to a per-component sign, and the reference's clamp threshold is a
 quantile over SIGNED values, so elementwise equality with LAPACK is not defined (SURVEY.md 7);
@@ -28,74 +30,65 @@ from ._C import check, dtype_code, ptr, stream_ptr
 L = 32
 
 
-def _ptr_array(tensors: Sequence[torch.Tensor], device) -> torch.Tensor:
-    return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=device)
-
-
-def _orth2(Y: torch.Tensor, G: torch.Tensor, V: torch.Tensor, sig: torch.Tensor, rows: int, batch: int,
-           sweeps: int = 6):
-    """Orthonormalise the 32 columns of Y in place, twice (like CholeskyQR2, but rank-revealing):
-    G = Y^T Y = V diag(s^2) V^T (Jacobi)  ->  Y <- Y V diag(1/s), numerically null directions
-    (s < 1e-6 s_max) become zero columns. A Cholesky factor would break down exactly there, and
-    exactly-low-rank deltas are a real input (a fine-tune that IS a merged LoRA)."""
-    lib, st = _C.lib, stream_ptr()
-    for _ in range(2):
-        check(lib.lb_svd_gram(ptr(Y), ptr(G), rows, batch, st), "lb_svd_gram")
-        check(lib.lb_svd_jacobi(ptr(G), ptr(V), ptr(sig), batch, sweeps, st), "lb_svd_jacobi")
-        check(lib.lb_svd_apply(ptr(Y), ptr(V), ptr(sig), 2, ptr(Y), rows, L, L, 0, rows * L, batch, st),
-              "lb_svd_apply")
-        ops._count(3)
+def svd_lowrank_ragged(W_tuned: Sequence[torch.Tensor], W_base: Sequence[torch.Tensor], rank: int,
+                       power_iters: int = 1, clamp_quantile: Optional[float] = None, seed: int = 0):
+    """ONE C call (lb_svd_truncated_batched) for any mix of 2-D weight shapes of one dtype
+    (fp32 / bf16 / fp16): returns ([up_b [N_b, rank] = U_r diag(S_r)], [down_b [rank, K_b] = Vh_r],
+    sigma [batch, 32] descending, hi [batch] or None). With clamp_quantile the reference's clamp
+    (cli_svd.py:43-47) is applied in the same call (exact radix-select quantile per matrix)."""
+    if not 1 <= rank <= 16:
+        raise _C.LoraB200Error("svd_lowrank: rank must be in [1,16]")
+    batch = len(W_tuned)
+    if batch == 0:
+        return [], [], None, None
+    w0 = W_tuned[0]
+    if not w0.is_cuda:
+        raise _C.LoraB200Error("svd_lowrank needs CUDA tensors (no CPU path)")
+    dev = w0.device
+    keep_t = [t.detach().contiguous() for t in W_tuned]
+    keep_b = [t.detach().contiguous() for t in W_base]
+    for t, bt in zip(keep_t, keep_b):
+        assert t.dim() == 2 and t.shape == bt.shape and t.dtype == w0.dtype and bt.dtype == w0.dtype
+    Ns = [int(t.shape[0]) for t in keep_t]
+    Ks = [int(t.shape[1]) for t in keep_t]
+    IA = ctypes.c_int * batch
+    VP = ctypes.c_void_p * batch
+    n_arr, k_arr = IA(*Ns), IA(*Ks)
+    wt_arr = VP(*[t.data_ptr() for t in keep_t])
+    wb_arr = VP(*[t.data_ptr() for t in keep_b])
+    wdt = dtype_code(w0.dtype)
+    lib = _C.lib
+    ws_bytes = int(lib.lb_svd_workspace_bytes(n_arr, k_arr, batch, wdt))
+    if ws_bytes <= 0:
+        raise _C.LoraB200Error(f"lb_svd_workspace_bytes failed: {ws_bytes}")
+    ws = torch.empty(ws_bytes, device=dev, dtype=torch.uint8)
+    offs, total = [], 0
+    for n, k in zip(Ns, Ks):
+        offs.append(total)
+        total += rank * (n + k)
+    out = torch.empty(total, device=dev, dtype=torch.float32)
+    sigma = torch.empty((batch, L), device=dev, dtype=torch.float32)
+    do_clamp = clamp_quantile is not None and clamp_quantile > 0.0
+    hi = torch.empty(batch, device=dev, dtype=torch.float32) if do_clamp else None
+    check(lib.lb_svd_truncated_batched(wt_arr, wb_arr, n_arr, k_arr, batch, wdt, rank, int(power_iters),
+                                       float(clamp_quantile) if do_clamp else -1.0,
+                                       ctypes.c_ulonglong(seed * 2654435761 + 12345), ptr(out), ptr(sigma),
+                                       ptr(hi), ptr(ws), ws_bytes, stream_ptr()),
+          "lb_svd_truncated_batched")
+    # launches: probes + (2q+2) passes + Gram/Jacobi/transform stages + factors x2 (+ clamp)
+    ops._count(1 + (2 * power_iters + 2) + 6 * power_iters + 7 + 2 + (1 if do_clamp else 0))
+    ups = [out[o:o + rank * n].view(n, rank) for o, n in zip(offs, Ns)]
+    downs = [out[o + rank * n:o + rank * (n + k)].view(rank, k) for o, n, k in zip(offs, Ns, Ks)]
+    return ups, downs, sigma, hi
 
 
 def svd_lowrank_batched(W_tuned: Sequence[torch.Tensor], W_base: Sequence[torch.Tensor], rank: int,
-                        power_iters: int = 2, seed: int = 0, jacobi_sweeps: int = 10
+                        power_iters: int = 1, seed: int = 0, jacobi_sweeps: int = 10
                         ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """Same-shape 2-D weight pairs -> (up [b,N,rank] = U_r diag(S_r), down [b,rank,K] = Vh_r,
     sigma [b,32] descending). Weights may be fp32 / bf16 / fp16 (all the same dtype)."""
-    if not 1 <= rank <= 16:
-        raise _C.LoraB200Error("svd_lowrank_batched: rank must be in [1,16]")
-    batch = len(W_tuned)
-    w0 = W_tuned[0]
-    if not w0.is_cuda:
-        raise _C.LoraB200Error("svd_lowrank_batched needs CUDA tensors (no CPU path)")
-    N, K = w0.shape
-    dev = w0.device
-    keep = [t.detach().contiguous() for t in list(W_tuned) + list(W_base)]
-    for t in keep:
-        assert t.shape == (N, K) and t.dtype == w0.dtype
-    pt, pb = _ptr_array(keep[:batch], dev), _ptr_array(keep[batch:], dev)
-    wdt = dtype_code(w0.dtype)
-    lib, st = _C.lib, stream_ptr()
-    f32 = dict(device=dev, dtype=torch.float32)
-    Z = torch.empty((batch, K, L), **f32)
-    Y = torch.empty((batch, N, L), **f32)
-    G = torch.empty((batch, L, L), **f32)
-    V = torch.empty((batch, L, L), **f32)
-    sigma = torch.empty((batch, L), **f32)
-
-    check(lib.lb_svd_randn(ptr(Z), Z.numel(), ctypes.c_ulonglong(seed * 2654435761 + 12345), st), "lb_svd_randn")
-    check(lib.lb_svd_mul(ptr(pt), ptr(pb), wdt, ptr(Z), ptr(Y), N, K, batch, 0, st), "lb_svd_mul")
-    ops._count(2)
-    _orth2(Y, G, V, sigma, N, batch)
-    for _ in range(power_iters):
-        check(lib.lb_svd_mul(ptr(pt), ptr(pb), wdt, ptr(Y), ptr(Z), N, K, batch, 1, st), "lb_svd_mul")
-        _orth2(Z, G, V, sigma, K, batch)
-        check(lib.lb_svd_mul(ptr(pt), ptr(pb), wdt, ptr(Z), ptr(Y), N, K, batch, 0, st), "lb_svd_mul")
-        _orth2(Y, G, V, sigma, N, batch)
-        ops._count(2)
-    # Q = Y (orthonormal); Z = dW^T Q = B^T ;  B B^T = Z^T Z = Uh diag(s^2) Uh^T
-    check(lib.lb_svd_mul(ptr(pt), ptr(pb), wdt, ptr(Y), ptr(Z), N, K, batch, 1, st), "lb_svd_mul")
-    check(lib.lb_svd_gram(ptr(Z), ptr(G), K, batch, st), "lb_svd_gram")
-    check(lib.lb_svd_jacobi(ptr(G), ptr(V), ptr(sigma), batch, jacobi_sweeps, st), "lb_svd_jacobi")
-    up = torch.empty((batch, N, rank), **f32)
-    down = torch.empty((batch, rank, K), **f32)
-    # up = (Q Uh)[:, :r] * s ;  down = ((Z Uh)[:, :r] / s)^T
-    check(lib.lb_svd_apply(ptr(Y), ptr(V), ptr(sigma), 1, ptr(up), N, rank, rank, 0, N * rank, batch, st),
-          "lb_svd_apply")
-    check(lib.lb_svd_apply(ptr(Z), ptr(V), ptr(sigma), 2, ptr(down), K, rank, K, 1, rank * K, batch, st),
-          "lb_svd_apply")
-    ops._count(5)
-    return up, down, sigma
+    ups, downs, sigma, _ = svd_lowrank_ragged(W_tuned, W_base, rank, power_iters=power_iters, seed=seed)
+    return torch.stack(ups), torch.stack(downs), sigma
 
 
 def _clamp_pair_(up: torch.Tensor, down: torch.Tensor, q: float):
@@ -113,7 +106,7 @@ def _iter_lora(model):
 
 
 def overwrite_base(base_model: nn.Module, tuned_model: nn.Module, rank: int, clamp_quantile: float,
-                   power_iters: int = 2, shard: Optional[Tuple[int, int]] = None):
+                   power_iters: int = 1, shard: Optional[Tuple[int, int]] = None):
     """cli_svd.py:24-92 on two LoRA-injected models with identical site structure: the factors of
     `base_model`'s sites are overwritten with the rank-`rank` distillation of (tuned - base).
 
@@ -131,17 +124,12 @@ def overwrite_base(base_model: nn.Module, tuned_model: nn.Module, rank: int, cla
         hb = sb.linear if hasattr(sb, "linear") else sb.conv
         ht = st_.linear if hasattr(st_, "linear") else st_.conv
         wb, wt = hb.weight.data, ht.weight.data
-        groups[(tuple(wb.shape), wb.dtype)].append((sb, wb.flatten(start_dim=1), wt.flatten(start_dim=1)))
-    for (shape, _), items in groups.items():
-        ups, downs, _ = svd_lowrank_batched([x[2] for x in items], [x[1] for x in items], rank,
-                                            power_iters=power_iters)
-        # cli_svd.py:42-47 for the whole group at once: hi_b = quantile(cat(U_b, Vh_b), q); clamp to [-hi_b, hi_b]
-        b = ups.shape[0]
-        hi = torch.quantile(torch.cat([ups.reshape(b, -1), downs.reshape(b, -1)], dim=1), clamp_quantile, dim=1)
-        ups = torch.minimum(torch.maximum(ups, -hi.view(b, 1, 1)), hi.view(b, 1, 1))
-        downs = torch.minimum(torch.maximum(downs, -hi.view(b, 1, 1)), hi.view(b, 1, 1))
-        for i, (site, _, _) in enumerate(items):
-            u, d = ups[i], downs[i]
+        groups[wb.dtype].append((sb, wb.flatten(start_dim=1), wt.flatten(start_dim=1)))
+    for _, items in groups.items():
+        # every site of this dtype -- whatever its shape -- in ONE call, clamp included
+        ups, downs, _, _ = svd_lowrank_ragged([x[2] for x in items], [x[1] for x in items], rank,
+                                              power_iters=power_iters, clamp_quantile=clamp_quantile)
+        for (site, _, _), u, d in zip(items, ups, downs):
             dev, dt = site.lora_up.weight.device, site.lora_up.weight.dtype
             assert site.lora_up.weight.flatten(1).shape == u.shape
             assert site.lora_down.weight.flatten(1).shape == d.shape

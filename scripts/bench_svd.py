@@ -10,7 +10,7 @@ import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from lora_b200.svd import svd_lowrank_batched
+from lora_b200.svd import svd_lowrank_ragged
 
 SHAPES = [(320, 320, 30), (2560, 320, 5), (320, 768, 10), (640, 640, 30), (5120, 640, 5), (640, 768, 10),
           (1280, 1280, 36), (10240, 1280, 6), (1280, 768, 12), (768, 768, 48)]
@@ -31,16 +31,24 @@ for (N, K, cnt) in SHAPES:
     n_mats += cnt
 
 
+ALL_T = [w for Wt, _ in groups for w in Wt]
+ALL_B = [w for _, Wb in groups for w in Wb]
+
+
 def run():
-    outs = []
-    for Wt, Wb in groups:
-        outs.append(svd_lowrank_batched(Wt, Wb, rank))
+    """ONE call for all 240 weight deltas (ragged over the 10 shapes), quantile clamp included."""
+    ups, downs, sigma, hi = svd_lowrank_ragged(ALL_T, ALL_B, rank, clamp_quantile=0.99)
+    outs, i = [], 0
+    for Wt, _ in groups:
+        n = len(Wt)
+        outs.append((ups[i:i + n], downs[i:i + n], sigma[i:i + n]))
+        i += n
     return outs
 
 
 run(); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-reps = 3
+reps = 5
 e0.record()
 for _ in range(reps):
     outs = run()
@@ -67,7 +75,7 @@ if os.path.exists("MEASURED_PEAKS.json"):
 out = {"workload": "SD1.5 svd_distill rank 8: 192 UNet attention/GEGLU + 48 CLIP weight deltas (fp16 pairs)",
        "matrices": n_mats, "ms_total": ms, "matrices_per_s": n_mats / ms * 1e3,
        "algorithmic_GBps": total_bytes / ms / 1e6, "frac_of_hbm_peak": total_bytes / ms / 1e6 / peak,
-       "passes_over_weights": 6, "max_rel_sigma_err": worst,
+       "passes_over_weights": 4, "max_rel_sigma_err": worst,
        "reference_way_ms_per_matrix_subset(torch.linalg.svd full, cuSOLVER)": ref_ms_per_mat,
        "reference_way_est_ms_total": ref_ms_per_mat * n_mats}
 print(json.dumps(out))

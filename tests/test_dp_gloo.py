@@ -69,17 +69,22 @@ def test_shard_indices_round_robin():
         assert seen == set(range(10))
 
 
-def _cpu_svd_stub(W_tuned, W_base, rank, power_iters=2):
-    """Exact truncated SVD on CPU standing in for the CUDA kernels (same return contract as
-    lora_b200.svd.svd_lowrank_batched): the test below is about WHICH process distils WHICH site and
-    how the factors travel, not about the factorisation."""
-    ups, downs, sig = [], [], []
+def _cpu_svd_stub(W_tuned, W_base, rank, power_iters=1, clamp_quantile=None, seed=0):
+    """Exact truncated SVD (+ the reference's quantile clamp) on CPU standing in for the CUDA call
+    (same return contract as lora_b200.svd.svd_lowrank_ragged): the test below is about WHICH
+    process distils WHICH site and how the factors travel, not about the factorisation."""
+    ups, downs, sig, his = [], [], [], []
     for wt, wb in zip(W_tuned, W_base):
         U, S, Vh = torch.linalg.svd(wt.float() - wb.float(), full_matrices=False)
-        ups.append(U[:, :rank] * S[:rank])
-        downs.append(Vh[:rank])
+        u, d = U[:, :rank] * S[:rank], Vh[:rank]
+        if clamp_quantile is not None:
+            hi = torch.quantile(torch.cat([u.flatten(), d.flatten()]), clamp_quantile)
+            u, d = u.clamp(-hi, hi), d.clamp(-hi, hi)
+            his.append(hi)
+        ups.append(u)
+        downs.append(d)
         sig.append(S[:rank])
-    return torch.stack(ups), torch.stack(downs), torch.stack(sig)
+    return ups, downs, sig, his
 
 
 def _build_pair():
@@ -110,10 +115,10 @@ def _svd_worker(rank, world, port, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     seen = []
-    def stub(W_tuned, W_base, r, power_iters=2):
+    def stub(W_tuned, W_base, r, power_iters=1, clamp_quantile=None, seed=0):
         seen.append(len(W_tuned))
-        return _cpu_svd_stub(W_tuned, W_base, r, power_iters)
-    svd.svd_lowrank_batched = stub
+        return _cpu_svd_stub(W_tuned, W_base, r, power_iters, clamp_quantile)
+    svd.svd_lowrank_ragged = stub
     base, tuned = _build_pair()
     svd.overwrite_base(base, tuned, rank=4, clamp_quantile=0.99, shard=(rank, world))
     torch.save({"factors": _factors(base), "n_done": sum(seen)}, os.path.join(out_dir, f"svd{rank}.pt"))
@@ -129,13 +134,13 @@ def test_sharded_svd_distill_equals_single_process(tmp_path):
     world = 2
     mp.spawn(_svd_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     outs = [torch.load(tmp_path / f"svd{r}.pt") for r in range(world)]
-    real = svd.svd_lowrank_batched
+    real = svd.svd_lowrank_ragged
     try:
-        svd.svd_lowrank_batched = _cpu_svd_stub
+        svd.svd_lowrank_ragged = _cpu_svd_stub
         base, tuned = _build_pair()
         svd.overwrite_base(base, tuned, rank=4, clamp_quantile=0.99)
     finally:
-        svd.svd_lowrank_batched = real
+        svd.svd_lowrank_ragged = real
     want = _factors(base)
     n_sites = len(want) // 2
     assert outs[0]["n_done"] + outs[1]["n_done"] == n_sites and abs(outs[0]["n_done"] - outs[1]["n_done"]) <= 1

@@ -167,7 +167,7 @@ def test_every_tile_schedule_gives_the_same_result(M, K, N, r, mode):
     finally:
         _C.lib.lb_debug_set_linear_mode(0)
     y0, t0, _ = run_fused(x, W, A, B, b, d, 0.9, torch.float32)
-    assert rel_err(t, t0) < 1e-6
+    assert rel_err(t, t0) < 3e-6       # fp32 summation order only (auto may pick a split-K plan)
     assert rel_err(y, y0) < 3e-4
     ref = O.lora_linear_forward(x, W, b, A, B, 0.9, diag=d)
     branch = (ref - O.lora_linear_forward(x, W, b, A, torch.zeros_like(B), 0.0)).norm()

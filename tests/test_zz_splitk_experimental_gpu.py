@@ -34,7 +34,7 @@ def test_cluster_splitk_matches_default_schedule(M, K, N, r, split, out_dtype):
     finally:
         _C.lib.lb_debug_set_linear_mode(0)
     y0, t0, _ = run_fused(x, W, A, B, b, d, 0.9, out_dtype)
-    assert rel_err(t, t0) < 1e-6
+    assert rel_err(t, t0) < 3e-6
     assert rel_err(y, y0) < (3e-4 if out_dtype == torch.float32 else 1e-2)
     if out_dtype == torch.float32:
         ref = O.lora_linear_forward(x, W, b, A, B, 0.9, diag=d)
@@ -52,4 +52,4 @@ def test_cluster_splitk_wide_tiles():
     finally:
         _C.lib.lb_debug_set_linear_mode(0)
     y0, t0, _ = run_fused(x, W, A, B, b, d, 1.0, torch.bfloat16)
-    assert rel_err(t, t0) < 1e-6 and rel_err(y, y0) < 1e-2
+    assert rel_err(t, t0) < 3e-6 and rel_err(y, y0) < 1e-2
