@@ -245,6 +245,18 @@ int lb_adamw_clip_step(float* p, float* g, float* m, float* v, long long n,
                        float beta2, float eps, float weight_decay, float max_norm, float inv_world,
                        int* step_dev, float* partials, float* gnorm_out, void* stream);
 
+/* The whole optimizer step in ONE cooperative launch: lb_adamw_clip_step's two passes plus
+ * lb_refresh_shadows (the re-cast of every LoRA factor into the 16-bit [16, C] operands of the
+ * fused kernels; `table` = the rows lb_refresh_shadows walks, n_entries may be 0), separated by
+ * grid barriers on `barrier2` (2 x uint32 of device memory, zero-initialised once by the caller).
+ * train_lora_dreambooth.py:878-888 (clip_grad_norm_, optimizer.step, zero_grad). */
+int lb_optim_step_fused(float* p, float* g, float* m, float* v, long long n,
+                        const long long* group_off, int n_groups, const float* lr_dev, float beta1,
+                        float beta2, float eps, float weight_decay, float max_norm, float inv_world,
+                        int* step_dev, float* partials, float* gnorm_out, const long long* table,
+                        int n_entries, int max_C, void* shadow16, int shadow_dtype,
+                        unsigned int* barrier2, void* stream);
+
 /* Batched 16-bit shadow refresh after an optimizer step: for every table entry e, j < 16, c < e.C
  *   dst16_base[e.dst_off + j*e.dst_rs + c] = (j < e.r) ? p[e.src_off + j*e.src_rs + c*e.src_cs] : 0
  * table: DEVICE array of n_entries x 7 long long {src_off, src_rs, src_cs, r, C, dst_off, dst_rs}.
@@ -293,6 +305,27 @@ int lb_svd_apply(const float* Y, const float* M, const float* colscale, int scal
 int lb_svd_jacobi(const float* G, float* V, float* sigma, int batch, int sweeps, void* stream);
 /* standard-normal probes from a counter hash */
 int lb_svd_randn(float* out, long long n, unsigned long long seed, void* stream);
+
+/* Step prologue, one launch (cli_lora_pti.py:295-313, train_lora_dreambooth.py:822-840):
+ *   out[b, h, w, c] = sqrt_acp[t_b] * latents[b, c, h, w] + sqrt_one_minus_acp[t_b] * noise[b, c, h, w]
+ * latents / noise fp32 NCHW, timesteps int64 [B], out NHWC (a channels_last [B, C', H, W] tensor) of
+ * out_dtype. With inpaint_mask [B,1,H,W] and masked_latents [B,C,H,W] (both or neither): C' = 2C + 1,
+ * out = cat([noisy, mask, masked_latents], channel) -- the 9-channel inpainting input. */
+int lb_step_prologue(const float* latents, const float* noise, const long long* timesteps,
+                     const float* sqrt_acp, const float* sqrt_one_minus_acp, int n_timesteps,
+                     const float* inpaint_mask, const float* masked_latents, void* out, int out_dtype,
+                     int B, int C, int H, int W, void* stream);
+
+/* Loss epilogue, one launch (cli_lora_pti.py:340-370, train_lora_dreambooth.py:855-875):
+ *   loss = sum_b weights[b] * mean_{c,h,w} (mask[b,h,w] * (pred - target))^2      (weights NULL: 1/B)
+ *   grad = d loss / d pred = 2 weights[b] mask^2 (pred - target) / (C H W)        (pred's dtype/layout)
+ * pred element (b, c, pixel) at b*stride_b + c*stride_c + pixel*stride_p (NCHW or channels_last);
+ * target fp32 NCHW; mask [B,1,H,W] fp32 (already normalised as in cli_lora_pti.py:356-364) or NULL.
+ * partials64: >= 64 floats of scratch; counter: one zero-initialised uint32 (self-resetting). */
+int lb_masked_mse_fwd_bwd(const void* pred, int pred_dtype, long long stride_b, long long stride_c,
+                          long long stride_p, const float* target, const float* mask,
+                          const float* weights, void* grad, float* loss, float* partials64,
+                          unsigned int* counter, int B, int C, int H, int W, void* stream);
 
 #ifdef __cplusplus
 }

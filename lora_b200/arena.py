@@ -79,6 +79,11 @@ class LoraArena:
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
         self.partials = torch.zeros(1024, device=dev, dtype=torch.float32)
         self.gnorm = torch.zeros(1, device=dev, dtype=torch.float32)
+        self._grid_bar = torch.zeros(2, device=dev, dtype=torch.int32)   # lb_optim_step_fused's grid barrier
+        # one cooperative launch for clip + AdamW + zero_grad + shadow refresh; LB_OPT_SPLIT=1 keeps
+        # the three separate launches (lb_adamw_clip_step x2 kernels + lb_refresh_shadows)
+        import os as _os
+        self.fused_step = _os.environ.get("LB_OPT_SPLIT", "0") != "1"
         self._group_off_c = (ctypes.c_longlong * len(self.group_off))(*self.group_off)
 
         # ---- adopt: Parameters become views of p; .grad views of g
@@ -198,7 +203,20 @@ class LoraArena:
 
     def step(self, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, max_norm=1.0,
              world_size: int = 1):
-        """clip_grad_norm_(max_norm) + AdamW + zero_grad on the (already summed) gradients."""
+        """clip_grad_norm_(max_norm) + AdamW + zero_grad on the (already summed) gradients, then the
+        16-bit operand shadows -- one cooperative launch (lb_optim_step_fused)."""
+        if self.fused_step:
+            check(_C.lib.lb_optim_step_fused(ptr(self.p), ptr(self.g), ptr(self.m), ptr(self.v), self.n,
+                                             self._group_off_c, len(self.group_off) - 1, ptr(self.lr),
+                                             beta1, beta2, eps, weight_decay,
+                                             float(max_norm if max_norm else 0.0), 1.0 / world_size,
+                                             ptr(self.step_dev), ptr(self.partials), ptr(self.gnorm),
+                                             ptr(self.table), self.table.shape[0], self.table_max_c,
+                                             ptr(self.shadow), dtype_code(self.compute_dtype),
+                                             ptr(self._grid_bar), stream_ptr()), "lb_optim_step_fused")
+            ops._count(1)
+            self._publish_shadows()
+            return
         check(_C.lib.lb_adamw_clip_step(ptr(self.p), ptr(self.g), ptr(self.m), ptr(self.v),
                                         self.n, self._group_off_c, len(self.group_off) - 1,
                                         ptr(self.lr), beta1, beta2, eps, weight_decay,

@@ -19,7 +19,7 @@ static int launch_conv(const void* X, const void* W, const void* Dn, void* Y, co
   if constexpr (SPLITK) {
     const size_t tiles = static_cast<size_t>((p.N + BLOCK_N - 1) / BLOCK_N) * n_img * p.tiles_h * p.tiles_w;
     p.split = split;
-    if (!split_ws_reserve(stream, tiles * split * BLOCK_M * (BLOCK_N + R_PAD * G) * sizeof(float),
+    if (!split_ws_reserve(stream, tiles * BLOCK_M * (BLOCK_N + R_PAD * G) * sizeof(float),
                           static_cast<unsigned int>(tiles), &p.ws, &p.counters))
       return LB_ERR_CUDA;
   }
@@ -53,12 +53,11 @@ static ConvPlan plan_conv_split(long long m_tiles, int num_kb, int N, int g, int
     if (t1 < base_t) base_t = t1;
     for (int sp = 2; sp <= 8; ++sp) {
       if (tiles * sp > n_sms || num_kb / sp < 4) break;
-      const double peer = (bn + 16.0 * g) * 512.0 / 92e3;
-      const double t = 2.0 + ((num_kb + sp - 1) / sp) * per_kb + 1.0 + (sp - 1) * peer;
+      const double t = 2.0 + ((num_kb + sp - 1) / sp) * per_kb + 3.0 + (g > 1 ? 2.0 : 0.0);
       if (t < best_t) { best_t = t; best = {bn, sp}; }
     }
   }
-  if (best.split > 1 && best_t < 0.85 * base_t) return best;
+  if (best.split > 1 && best_t < 0.75 * base_t) return best;
   return {0, 1};
 }
 

@@ -57,10 +57,10 @@ struct FusedParams {
   float drop_p, drop_inv;
   const unsigned long long* seed;
   // split-K (SPLITK kernels only): gridDim.z = split CTAs share one output tile, each reducing a
-  // contiguous range of K blocks; partial accumulators ([split][128][BLOCK_N + 16 G] fp32 per tile)
-  // go through `ws` (L2-resident), `counters[tile]` elects the last CTA to arrive, which adds the
-  // other partials to its own TMEM accumulator and runs the ordinary epilogue. Counters must be 0
-  // on entry and are reset by the elected CTA.
+  // contiguous range of K blocks. Every CTA adds its partial accumulator (base + T columns) into the
+  // tile's [128][BLOCK_N + 16 G] fp32 buffer in `ws` with vector reductions at L2; `counters[tile]`
+  // elects the last CTA to arrive, which reads the reduced row back in one burst, wipes it and runs
+  // the ordinary epilogue. Buffer and counters must be zero on entry; the elected CTA leaves them so.
   int split;
   float* ws;
   unsigned int* counters;
@@ -252,6 +252,8 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
         const uint64_t bd = umma_smem_desc(sbase + S::OFF_UP + g * 256, 128, 256 * G, 0);
         if constexpr (DROP)
           umma_f16_ss(tmem + S::L_COL0, ad, bd, idesc_base, g != 0);   // own columns (masked in the drain)
+        else if constexpr (SPLITK)
+          umma_f16_ss(tmem, ad, bd, idesc_base, g != 0);   // the base partial lives in the reduced row
         else
           umma_f16_ss(tmem, ad, bd, idesc_base, 1);
       }
@@ -302,72 +304,60 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
     tc_fence_after();
     const uint32_t lane_base = tmem + (static_cast<uint32_t>(q * 32) << 16);
     bool elected = true;          // split-K: is this the CTA that finishes the tile?
-    const float* peers = nullptr; // split-K: this tile's [split][128][PCOLS] partials
-    int my_rank = 0;
+    float* acc_row = nullptr;     // split-K: this thread's row of the tile's fp32 accumulation buffer
     auto tap_touched = [&](int g) {   // did this CTA's K range feed tap g's T columns?
       return !SPLITK || G == 1 || (kb_begin < (g + 1) * cblocks && kb_end > g * cblocks);
     };
-    // sum of the OTHER CTAs' partials for 16 columns of this thread's row (L2 reads, 4 peers in flight)
-    auto add_peers16 = [&](float (&acc)[16], int col0) {
-      for (int s0 = 0; s0 < p.split; s0 += 4) {
-        float4 buf[4][4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int sp = s0 + u;
-          const bool ok = sp < p.split && sp != my_rank;
-          const float4* src = reinterpret_cast<const float4*>(
-              peers + (static_cast<size_t>(ok ? sp : 0) * BLOCK_M + row) * PCOLS + col0);
-#pragma unroll
-          for (int w4 = 0; w4 < 4; ++w4) buf[u][w4] = ok ? __ldcg(src + w4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-#pragma unroll
-          for (int w4 = 0; w4 < 4; ++w4) {
-            acc[4 * w4 + 0] += buf[u][w4].x; acc[4 * w4 + 1] += buf[u][w4].y;
-            acc[4 * w4 + 2] += buf[u][w4].z; acc[4 * w4 + 3] += buf[u][w4].w;
-          }
-      }
-    };
+    // split-K, G == 1: the whole reduced row (base + T columns) in registers after ONE burst of L2
+    // reads; G > 1 (conv dX): T groups first, base columns chunk by chunk in the drain
+    constexpr int ROW_REGS = (SPLITK && G == 1) ? PCOLS : 1;
+    float rowv[ROW_REGS];
     if constexpr (SPLITK) {
-      my_rank = blockIdx.z;
       const unsigned tile_id = blockIdx.y * gridDim.x + blockIdx.x;
-      float* tile_ws = p.ws + static_cast<size_t>(tile_id) * p.split * (BLOCK_M * PCOLS);
-      peers = tile_ws;
-      float* mine = tile_ws + (static_cast<size_t>(my_rank) * BLOCK_M + row) * PCOLS;
-      // own partial -> workspace, 16 columns at a time (T columns of taps this CTA never fed: zeros)
+      acc_row = p.ws + (static_cast<size_t>(tile_id) * BLOCK_M + row) * PCOLS;
+      // every CTA adds its partial into the tile's accumulation buffer (vector fp32 reductions at
+      // L2, fire-and-forget); T columns of taps this CTA never fed are skipped
 #pragma unroll 1
       for (int c = 0; c < PCOLS / 16; ++c) {
+        if (c >= BLOCK_N / 16 && (p.t_in != nullptr || !tap_touched(c - BLOCK_N / 16))) continue;
         uint32_t v[16];
-        const bool live = c < BLOCK_N / 16 || tap_touched(c - BLOCK_N / 16);
-        if (live) {
-          tmem_ld16(lane_base + c * 16, v);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = 0u;
-        }
-        float4* dst = reinterpret_cast<float4*>(mine + c * 16);
+        tmem_ld16(lane_base + c * 16, v);
+        tmem_ld_wait();
 #pragma unroll
         for (int w4 = 0; w4 < 4; ++w4)
-          dst[w4] = make_float4(__uint_as_float(v[4 * w4]), __uint_as_float(v[4 * w4 + 1]),
-                                __uint_as_float(v[4 * w4 + 2]), __uint_as_float(v[4 * w4 + 3]));
+          asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
+                       ::"l"(acc_row + c * 16 + w4 * 4), "f"(__uint_as_float(v[4 * w4])),
+                         "f"(__uint_as_float(v[4 * w4 + 1])), "f"(__uint_as_float(v[4 * w4 + 2])),
+                         "f"(__uint_as_float(v[4 * w4 + 3]))
+                       : "memory");
       }
-      __threadfence();                               // partial visible device-wide before the count
-      named_bar_sync(1, EPI_THREADS);
+      named_bar_sync(1, EPI_THREADS);                  // all 128 rows issued
       volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(sgen + S::OFF_TMEM + 4);
       if (et == 0) {
+        __threadfence();                               // cumulative: the CTA's reductions before the count
         const unsigned old = atomicAdd(p.counters + tile_id, 1u);
         const bool last = old == static_cast<unsigned>(p.split - 1);
-        if (last) p.counters[tile_id] = 0u;           // ready for the next launch on this stream
-        *flag = last ? 1u : 0u;
+        if (last) p.counters[tile_id] = 0u;            // ready for the next launch on this stream
         __threadfence();
+        *flag = last ? 1u : 0u;
       }
       named_bar_sync(1, EPI_THREADS);
       elected = *flag != 0u;
-      if (!elected) {                                 // partial delivered: release the MMA warp and leave
+      if (!elected) {                                  // partial delivered: release the MMA warp and leave
         tc_fence_before();
         mbar_arrive(bar_tready);
+      } else if constexpr (G == 1) {
+        // one burst: the reduced row (all CTAs' partials, this one's included), then wipe it for
+        // the next launch that gets this workspace region
+        const float4* src = reinterpret_cast<const float4*>(acc_row);
+#pragma unroll
+        for (int i = 0; i < PCOLS / 4; ++i) {
+          const float4 t4 = __ldcg(src + i);
+          rowv[4 * i] = t4.x; rowv[4 * i + 1] = t4.y; rowv[4 * i + 2] = t4.z; rowv[4 * i + 3] = t4.w;
+        }
+        float4* dstz = reinterpret_cast<float4*>(acc_row);
+#pragma unroll
+        for (int i = 0; i < PCOLS / 4; ++i) __stcg(dstz + i, make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
     if (elected) {
@@ -375,17 +365,26 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
     for (int g = 0; g < G; ++g) {
       float t[R_PAD];
       if (p.t_in == nullptr) {
-        if (tap_touched(g)) {
+        if constexpr (SPLITK) {
+          if constexpr (G == 1) {
+#pragma unroll
+            for (int j = 0; j < R_PAD; ++j) t[j] = rowv[BLOCK_N + j];
+          } else {
+            float4* src = reinterpret_cast<float4*>(acc_row + BLOCK_N + R_PAD * g);
+#pragma unroll
+            for (int w4 = 0; w4 < 4; ++w4) {
+              const float4 t4 = __ldcg(src + w4);
+              t[4 * w4] = t4.x; t[4 * w4 + 1] = t4.y; t[4 * w4 + 2] = t4.z; t[4 * w4 + 3] = t4.w;
+              __stcg(src + w4, make_float4(0.f, 0.f, 0.f, 0.f));
+            }
+          }
+        } else {
           uint32_t tv[R_PAD];
           tmem_ld16(lane_base + BLOCK_N + R_PAD * g, tv);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < R_PAD; ++j) t[j] = __uint_as_float(tv[j]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < R_PAD; ++j) t[j] = 0.f;
         }
-        if constexpr (SPLITK) add_peers16(t, BLOCK_N + R_PAD * g);
       } else {
         long long srow = grow;
         if constexpr (CONV && G > 1) {   // group g = tap g: the pixel shifted by (dy - pad, dx - pad)
@@ -435,8 +434,7 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
       ds1 = static_cast<uint32_t>(sd >> 32);
       dthr = drop_threshold(p.drop_p);
     }
-#pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
+    auto drain_chunk = [&](const int c) {
       uint32_t v[32];
       tmem_ld32(lane_base + c * 32, v);
       float f[32];
@@ -446,13 +444,24 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bias_s[c * 32 + j];
       if constexpr (SPLITK) {
-        float lo16[16], hi16[16];
+        // TMEM holds only the LoRA product here (its MMA overwrote this CTA's own partial, which is
+        // already inside the reduced row); non-DROP: v = T'.U^T, DROP: v is stale and ignored
+        if constexpr (G == 1) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { lo16[j] = f[j]; hi16[j] = f[16 + j]; }
-        add_peers16(lo16, c * 32);
-        add_peers16(hi16, c * 32 + 16);
+          for (int j = 0; j < 32; ++j)
+            f[j] = (DROP ? 0.f : __uint_as_float(v[j])) + bias_s[c * 32 + j] + rowv[c * 32 + j];
+        } else {
+          float4* src = reinterpret_cast<float4*>(acc_row + c * 32);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { f[j] = lo16[j]; f[16 + j] = hi16[j]; }
+          for (int w4 = 0; w4 < 8; ++w4) {
+            const float4 t4 = __ldcg(src + w4);
+            f[4 * w4] = (DROP ? 0.f : __uint_as_float(v[4 * w4])) + bias_s[c * 32 + 4 * w4] + t4.x;
+            f[4 * w4 + 1] = (DROP ? 0.f : __uint_as_float(v[4 * w4 + 1])) + bias_s[c * 32 + 4 * w4 + 1] + t4.y;
+            f[4 * w4 + 2] = (DROP ? 0.f : __uint_as_float(v[4 * w4 + 2])) + bias_s[c * 32 + 4 * w4 + 2] + t4.z;
+            f[4 * w4 + 3] = (DROP ? 0.f : __uint_as_float(v[4 * w4 + 3])) + bias_s[c * 32 + 4 * w4 + 3] + t4.w;
+            __stcg(src + w4, make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+        }
       }
       if constexpr (DROP) {
         // element index row*N + n; N % 8 == 0 and the chunk starts at a multiple of 32, so the
@@ -487,6 +496,13 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
                        __float_as_uint(f[qq * 4 + 3]));
         }
       }
+        };
+    if constexpr (SPLITK && G == 1) {   // fully unrolled: the reduced row is indexed statically (registers)
+#pragma unroll
+      for (int c = 0; c < BLOCK_N / 32; ++c) drain_chunk(c);
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) drain_chunk(c);
     }
     tc_fence_before();
     fence_proxy_async_smem();

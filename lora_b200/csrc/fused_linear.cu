@@ -19,7 +19,7 @@ static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, 
   if constexpr (SPLITK) {
     const size_t tiles = static_cast<size_t>((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + BLOCK_M - 1) / BLOCK_M);
     p.split = split;
-    if (!split_ws_reserve(stream, tiles * split * BLOCK_M * (BLOCK_N + R_PAD) * sizeof(float),
+    if (!split_ws_reserve(stream, tiles * BLOCK_M * (BLOCK_N + R_PAD) * sizeof(float),
                           static_cast<unsigned int>(tiles), &p.ws, &p.counters))
       return LB_ERR_CUDA;
   }
@@ -41,9 +41,9 @@ static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, 
 // Split-K plan for one linear problem (fused_core.cuh, SPLITK): the per-SM operand ingest (~92 GB/s
 // measured) makes a lone CTA's K loop cost ~0.29 us (BLOCK_N 64) / ~0.38 us (128) per
 // 64-wide K block, so sites with few tiles and long K leave most SMs idle while a handful stream.
-// Cost model in microseconds: fixed 2.0 (prologue + tail) + blocks x ingest; a split adds ~1.0
-// (publish + election) + the elected CTA's reads of the other partials (fp32, same ingest limit).
-// Only single-wave plans (tiles x split <= SMs) are considered, and a split must win by > 15 %.
+// Cost model in microseconds: fixed 2.0 (prologue + tail) + blocks x ingest; a split adds ~3.0
+// (L2 reductions of the partials, election, one burst read of the reduced row), independent of the
+// split factor. Only single-wave plans (tiles x split <= SMs), and a split must win by > 25 %.
 struct SplitPlan { int block_n, split; };
 static SplitPlan plan_split(int M, int K, int N, int n_sms) {
   if (!splitk_enabled() || n_sms <= 0) return {0, 1};
@@ -59,12 +59,11 @@ static SplitPlan plan_split(int M, int K, int N, int n_sms) {
     if (t1 < base_t) base_t = t1;
     for (int sp = 2; sp <= 8; ++sp) {
       if (tiles * sp > n_sms || num_kb / sp < 4) break;
-      const double peer = (bn + 16.0) * 512.0 / 92e3;
-      const double t = 2.0 + ((num_kb + sp - 1) / sp) * per_kb + 1.0 + (sp - 1) * peer;
+      const double t = 2.0 + ((num_kb + sp - 1) / sp) * per_kb + 3.0;
       if (t < best_t) { best_t = t; best = {bn, sp}; }
     }
   }
-  if (best.split > 1 && best_t < 0.85 * base_t) return best;
+  if (best.split > 1 && best_t < 0.75 * base_t) return best;
   return {0, 1};
 }
 

@@ -218,40 +218,81 @@ up_dropout_kernel(YT* __restrict__ Y, int y_fmt, const float* __restrict__ T,
   }
 }
 
-// dTs[m, j] = sum_n keep(m,n)/(1-p) * gY[m,n] * up[n, j]     (one warp per row)
+// dTs[m, j] = sum_n keep(m,n)/(1-p) * gY[m,n] * up[n, j]
+// CTA = 8 warps over a [32-row x 512-column] slab of gY; the slab's up rows are staged transposed
+// in shared memory ([j][n]: lanes read consecutive n), a lane owns 16 consecutive columns (two
+// 16-byte loads, 8 pair-hashes), a warp owns 4 rows and re-uses the staged factors across them.
+// Column slabs are combined with fp32 atomics (dTs zeroed by the launcher when there are several),
+// so small-M sites (the 8x8 convs, time_emb_proj with M = 1) still spread over the chip.
+constexpr int DT_ROWS = 32, DT_COLS = 512;
 __global__ void __launch_bounds__(256)
-dropout_dt_kernel(const uint32_t* __restrict__ gY, int fmt, const float* __restrict__ up,
+dropout_dt_kernel(const uint4* __restrict__ gY, int fmt, const float* __restrict__ up,
                   long long up_rs, long long up_cs, float drop_p,
                   const unsigned long long* __restrict__ seed_dev, float* __restrict__ dTs, int M,
-                  int N, int r) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= M) return;
-  const int m = warp;
-  const unsigned long long sd = seed_dev[0];
-  const float inv = 1.f / (1.f - drop_p);
-  float acc[16];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-  const size_t pitch = static_cast<size_t>(N) >> 1;
-  for (int n = lane * 2; n < N; n += 64) {
-    float2 g = ld16x2(__ldg(gY + static_cast<size_t>(m) * pitch + (n >> 1)), fmt);
-    const unsigned long long e = static_cast<unsigned long long>(m) * N + n;
-    g.x = drop_keep(sd, e, drop_p) ? g.x * inv : 0.f;
-    g.y = drop_keep(sd, e + 1, drop_p) ? g.y * inv : 0.f;
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (j < r) acc[j] += g.x * __ldg(up + n * up_rs + j * up_cs) + g.y * __ldg(up + (n + 1) * up_rs + j * up_cs);
+                  int N, int r, int use_atomics) {
+  __shared__ float ups[16][DT_COLS + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_base = blockIdx.x * DT_COLS;
+  const int m_base = blockIdx.y * DT_ROWS + warp * 4;
+  for (int i = threadIdx.x; i < 16 * DT_COLS; i += 256) {
+    const int j = i / DT_COLS, c = i % DT_COLS;
+    const int n = n_base + c;
+    // column c = lane*16 + 4q + w is stored at (q*32 + lane)*4 + w: a warp's float4 reads are contiguous
+    const int pos = ((((c >> 2) & 3) * 32 + (c >> 4)) << 2) + (c & 3);
+    ups[j][pos] = (j < r && n < N) ? __ldg(up + n * up_rs + j * up_cs) : 0.f;
   }
+  __syncthreads();
+  const unsigned long long sd = seed_dev[0];
+  const uint32_t s0 = static_cast<uint32_t>(sd), s1 = static_cast<uint32_t>(sd >> 32);
+  const uint32_t thr = drop_threshold(drop_p);
+  const float inv = 1.f / (1.f - drop_p);
+  const int c0 = lane * 16, n0 = n_base + c0;
+  const size_t pitch = static_cast<size_t>(N) >> 3;           // row pitch in 16-byte words
+  float g[4][16];
 #pragma unroll
-  for (int j = 0; j < 16; ++j)
+  for (int rr = 0; rr < 4; ++rr) {
+    const int m = m_base + rr;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-  if (lane == 0) {
-    float4* dst = reinterpret_cast<float4*>(dTs + static_cast<size_t>(m) * 16);
-    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-    dst[2] = make_float4(acc[8], acc[9], acc[10], acc[11]);
-    dst[3] = make_float4(acc[12], acc[13], acc[14], acc[15]);
+    for (int h = 0; h < 2; ++h) {
+      const int n = n0 + 8 * h;
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      if (m < M && n < N) raw = __ldg(gY + static_cast<size_t>(m) * pitch + (n >> 3));
+      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+      const unsigned long long e = (static_cast<unsigned long long>(m) * N + n) >> 1;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 v = ld16x2(w[q], fmt);
+        const uint32_t bits = drop_bits(s0, s1, e + q);
+        g[rr][8 * h + 2 * q] = (bits & 0xffffu) >= thr ? v.x * inv : 0.f;
+        g[rr][8 * h + 2 * q + 1] = (bits >> 16) >= thr ? v.y * inv : 0.f;
+      }
+    }
+  }
+  for (int j = 0; j < r; ++j) {
+    float u[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(&ups[j][(q * 32 + lane) << 2]);
+      u[4 * q] = t.x; u[4 * q + 1] = t.y; u[4 * q + 2] = t.z; u[4 * q + 3] = t.w;
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc += g[rr][c] * u[c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const int m = m_base + rr;
+      if (lane == 0 && m < M) {
+        if (use_atomics) atomicAdd(dTs + static_cast<size_t>(m) * 16 + j, acc);
+        else dTs[static_cast<size_t>(m) * 16 + j] = acc;
+      }
+    }
+  }
+  if (!use_atomics && lane < 16 && lane >= r) {                 // padded ranks stay zero
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr)
+      if (m_base + rr < M) dTs[static_cast<size_t>(m_base + rr) * 16 + lane] = 0.f;
   }
 }
 
@@ -460,6 +501,122 @@ adamw_update_kernel(float* __restrict__ p, float* __restrict__ g, float* __restr
     m[i] = mm;
     v[i] = vv;
     g[i] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------- one-launch optimizer step
+// clip_grad_norm_ + AdamW + zero_grad + refresh of the 16-bit operand shadows in ONE cooperative
+// launch (train_lora_dreambooth.py:878-888 is ~10 foreach launches over hundreds of tiny tensors):
+//   phase 1  per-block partial sum of g^2 (fixed order => deterministic)          -- grid barrier --
+//   phase 2  every block re-reduces the partials, forms coef, updates its slice of p/m/v, zeroes g
+//                                                                                  -- grid barrier --
+//   phase 3  re-casts every LoRA factor into the zero-padded 16-bit [16, C] operands the tcgen05
+//            kernels read (table walk, same rows as lb_refresh_shadows)
+// The grid is launched with cudaLaunchAttributeCooperative (co-residency guaranteed) and at most
+// one CTA per SM; the barrier is a generation counter in `bar` (2 x uint32, zero-initialised).
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int gen = atomicAdd(&bar[1], 0u);
+    if (atomicAdd(&bar[0], 1u) == nblocks - 1) {
+      bar[0] = 0u;
+      __threadfence();
+      atomicAdd(&bar[1], 1u);
+    } else {
+      const long long t0 = clock64();
+      while (atomicAdd(&bar[1], 0u) == gen) {
+        if (clock64() - t0 > 4000000000ll) __trap();   // a protocol bug traps instead of hanging the box
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(OPT_THREADS)
+optim_step_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                        float* __restrict__ v, long long n, OptGroups groups,
+                        const float* __restrict__ lr_dev, float beta1, float beta2, float eps, float wd,
+                        float max_norm, float inv_world, int* __restrict__ step_dev,
+                        float* __restrict__ partials, float* __restrict__ gnorm_out,
+                        const long long* __restrict__ table, int n_entries, int max_c,
+                        uint16_t* __restrict__ shadow, int fmt, unsigned int* __restrict__ bar) {
+  __shared__ float sh[OPT_THREADS / 32];
+  const unsigned int nb = gridDim.x;
+  // ---- phase 1
+  {
+    float s = 0.f;
+    const long long n4 = n >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (long long i = blockIdx.x * static_cast<long long>(OPT_THREADS) + threadIdx.x; i < n4;
+         i += static_cast<long long>(nb) * OPT_THREADS) {
+      const float4 x = g4[i];
+      s += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+      const float x = g[(n4 << 2) + threadIdx.x];
+      s += x * x;
+    }
+    const float tot = block_sum(s, sh);
+    if (threadIdx.x == 0) {
+      partials[blockIdx.x] = tot;
+      if (blockIdx.x == 0) step_dev[0] += 1;
+    }
+  }
+  grid_barrier(bar, nb);
+  // ---- phase 2
+  {
+    float s = 0.f;
+    for (unsigned int i = threadIdx.x; i < nb; i += OPT_THREADS) s += __ldcg(partials + i);
+    const float sq = block_sum(s, sh);
+    const float total = sqrtf(sq) * inv_world;
+    float coef = inv_world;
+    if (max_norm > 0.f) coef *= fminf(1.f, max_norm / (total + 1e-6f));
+    if (blockIdx.x == 0 && threadIdx.x == 0 && gnorm_out) gnorm_out[0] = total;
+    const int t = __ldcg(step_dev);
+    const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), static_cast<double>(t)));
+    const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(t))));
+    for (long long i = blockIdx.x * static_cast<long long>(OPT_THREADS) + threadIdx.x; i < n;
+         i += static_cast<long long>(nb) * OPT_THREADS) {
+      int gi = 0;
+#pragma unroll
+      for (int k = 1; k < OPT_MAX_GROUPS; ++k)
+        if (k < groups.n && i >= groups.off[k]) gi = k;
+      const float lr = lr_dev[gi];
+      const float gg = g[i] * coef;
+      float pp = p[i];
+      pp *= (1.f - lr * wd);
+      const float mm = beta1 * m[i] + (1.f - beta1) * gg;
+      const float vv = beta2 * v[i] + (1.f - beta2) * gg * gg;
+      const float denom = sqrtf(vv) / bc2_sqrt + eps;
+      pp -= (lr / bc1) * (mm / denom);
+      p[i] = pp;
+      m[i] = mm;
+      v[i] = vv;
+      g[i] = 0.f;
+    }
+  }
+  if (n_entries <= 0) return;
+  grid_barrier(bar, nb);
+  // ---- phase 3: work item = (table entry, 256-column block); p is read through L2 (just written)
+  {
+    const int cblocks = (max_c + OPT_THREADS - 1) / OPT_THREADS;
+    const long long items = static_cast<long long>(n_entries) * cblocks;
+    for (long long it = blockIdx.x; it < items; it += nb) {
+      const int e_i = static_cast<int>(it / cblocks), cb = static_cast<int>(it % cblocks);
+      const long long* e = table + static_cast<size_t>(e_i) * 7;
+      const long long src_off = e[0], rs = e[1], cs = e[2];
+      const int r = static_cast<int>(e[3]), C = static_cast<int>(e[4]);
+      const long long dst_off = e[5], dst_rs = e[6];
+      const int c = cb * OPT_THREADS + threadIdx.x;
+      if (c >= C) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float x = (j < r) ? __ldcg(p + src_off + j * rs + c * cs) : 0.f;
+        shadow[dst_off + j * dst_rs + c] = to16(x, fmt);
+      }
+    }
   }
 }
 
@@ -687,10 +844,15 @@ extern "C" int lb_lora_dropout_dt(const void* gY, int in_dtype, const float* up,
   if (r < 1 || r > 16) return LB_ERR_RANK;
   if (in_dtype != LB_BF16 && in_dtype != LB_F16) return LB_ERR_DTYPE;
   if (!(drop_p >= 0.f && drop_p < 1.f) || seed_dev == nullptr) return LB_ERR_SHAPE;
-  const int blocks = (M + 7) / 8;  // 8 warps per block, one row per warp
-  dropout_dt_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const uint32_t*>(gY), in_dtype == LB_BF16, up, up_rs, up_cs, drop_p,
-      reinterpret_cast<const unsigned long long*>(seed_dev), dTs, M, N, r);
+  if (reinterpret_cast<uintptr_t>(gY) & 15) return LB_ERR_ALIGN;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((N + DT_COLS - 1) / DT_COLS, (M + DT_ROWS - 1) / DT_ROWS);
+  const int use_atomics = grid.x > 1;
+  if (use_atomics && cudaMemsetAsync(dTs, 0, sizeof(float) * static_cast<size_t>(M) * 16, st) != cudaSuccess)
+    return LB_ERR_CUDA;
+  dropout_dt_kernel<<<grid, 256, 0, st>>>(
+      reinterpret_cast<const uint4*>(gY), in_dtype == LB_BF16, up, up_rs, up_cs, drop_p,
+      reinterpret_cast<const unsigned long long*>(seed_dev), dTs, M, N, r, use_atomics);
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }
 
@@ -813,4 +975,45 @@ extern "C" int lb_adamw_clip_step(float* p, float* g, float* m, float* v, long l
                                                      eps, weight_decay, max_norm, inv_world,
                                                      step_dev, partials, nblk, gnorm_out);
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
+extern "C" int lb_optim_step_fused(float* p, float* g, float* m, float* v, long long n,
+                                   const long long* group_off, int n_groups, const float* lr_dev,
+                                   float beta1, float beta2, float eps, float weight_decay,
+                                   float max_norm, float inv_world, int* step_dev, float* partials,
+                                   float* gnorm_out, const long long* table, int n_entries, int max_C,
+                                   void* shadow16, int shadow_dtype, unsigned int* barrier2,
+                                   void* stream) {
+  if (n <= 0 || n_groups < 1 || n_groups > OPT_MAX_GROUPS) return LB_ERR_SHAPE;
+  if (reinterpret_cast<uintptr_t>(g) & 15) return LB_ERR_ALIGN;
+  if (n_entries > 0 && (table == nullptr || shadow16 == nullptr || max_C <= 0)) return LB_ERR_SHAPE;
+  if (n_entries > 0 && shadow_dtype != LB_BF16 && shadow_dtype != LB_F16) return LB_ERR_DTYPE;
+  if (barrier2 == nullptr || partials == nullptr) return LB_ERR_SHAPE;
+  OptGroups groups;
+  groups.n = n_groups;
+  for (int i = 0; i <= n_groups; ++i) groups.off[i] = group_off[i];
+  for (int i = n_groups + 1; i <= OPT_MAX_GROUPS; ++i) groups.off[i] = n;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+    return LB_ERR_CUDA;
+  long long want = (n + OPT_THREADS - 1) / OPT_THREADS;
+  int nblk = static_cast<int>(want < 1 ? 1 : (want > sms ? sms : want));
+  if (nblk > OPT_MAX_PARTIALS) nblk = OPT_MAX_PARTIALS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nblk);
+  cfg.blockDim = dim3(OPT_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int fmt = shadow_dtype == LB_BF16;
+  uint16_t* sh = reinterpret_cast<uint16_t*>(shadow16);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, optim_step_fused_kernel, p, g, m, v, n, groups, lr_dev, beta1, beta2,
+                                     eps, weight_decay, max_norm, inv_world, step_dev, partials, gnorm_out,
+                                     table, n_entries, max_C, sh, fmt, barrier2);
+  return e == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }

@@ -82,7 +82,8 @@ inline bool splitk_enabled() {
   return v != 0;
 }
 
-// Split-K workspace (fused_core.cuh, SPLITK): one allocation per device, handed out as a ring so
+// Split-K workspace (fused_core.cuh, SPLITK): per-tile fp32 accumulation buffers, zero on entry
+// and wiped by the kernel that used them. One allocation per device, handed out as a ring so
 // that consecutive launches never share a region (a launch is stream-ordered after the previous
 // user of its region as long as fewer than ~4 launches run concurrently). Allocated at the first
 // split-K launch -- which must not happen inside a stream capture (cudaMalloc is illegal there);
@@ -105,6 +106,7 @@ inline bool split_ws_reserve(cudaStream_t stream, size_t need_bytes, unsigned in
     const size_t bytes = size_t(96) << 20;
     const unsigned int n = 1u << 16;
     if (cudaMalloc(&w.buf, bytes) != cudaSuccess) return false;
+    if (cudaMemset(w.buf, 0, bytes) != cudaSuccess) return false;   // accumulation buffers start at zero
     if (cudaMalloc(&w.counters, n * sizeof(unsigned int)) != cudaSuccess) return false;
     if (cudaMemset(w.counters, 0, n * sizeof(unsigned int)) != cudaSuccess) return false;
     w.bytes = bytes;

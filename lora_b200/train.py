@@ -77,6 +77,9 @@ class StepConfig:
     # buffers) instead of drawing them inside the step: lets a parity test or a replayed trace feed
     # the SAME draws to this engine and to the reference step, eager or graph-replayed
     external_noise: bool = False
+    # the step's prologue (add_noise + cast + channels_last [+ inpainting concat]) and loss epilogue
+    # ((masked) MSE + its gradient) as one kernel each (step_ops.py) instead of ~10 small torch ops
+    fused_glue: bool = True
 
 
 class LoraTrainStep:
@@ -134,9 +137,16 @@ class LoraTrainStep:
             noise = torch.randn_like(lat)
             t_max = int(self.noiser.num_train_timesteps * cfg.t_multiplier)
             timesteps = torch.randint(0, t_max, (bsz,), device=lat.device).long()
-        noisy = self.noiser.add_noise(lat, noise, timesteps)
-        if cfg.train_inpainting:
-            noisy = torch.cat([noisy, self.inpaint_mask.to(noisy.dtype), self.masked_latents.to(noisy.dtype)], dim=1)
+        fused = cfg.fused_glue and lat.is_cuda
+        if fused:
+            from .step_ops import step_prologue
+            noisy = step_prologue(lat, noise, timesteps, self.noiser, self.model_dtype,
+                                  self.inpaint_mask if cfg.train_inpainting else None,
+                                  self.masked_latents if cfg.train_inpainting else None)
+        else:
+            noisy = self.noiser.add_noise(lat, noise, timesteps)
+            if cfg.train_inpainting:
+                noisy = torch.cat([noisy, self.inpaint_mask.to(noisy.dtype), self.masked_latents.to(noisy.dtype)], dim=1)
         ac = (torch.autocast("cuda", dtype=cfg.autocast_dtype) if cfg.autocast_dtype is not None
               else torch.autocast("cuda", enabled=False))
         with ac:
@@ -145,22 +155,34 @@ class LoraTrainStep:
             else:
                 with torch.no_grad():
                     ehs = self.text_encoder(self.input_ids)[0]
-            noisy = noisy.to(self.model_dtype).contiguous(memory_format=torch.channels_last)
+            if not fused:
+                noisy = noisy.to(self.model_dtype).contiguous(memory_format=torch.channels_last)
             pred = self.unet(noisy, timesteps, ehs.to(self.model_dtype)).sample
         target = noise
+        m = None
         if cfg.use_mask:
             m = (self.mask.float() + 0.01).pow(cfg.mask_temperature)
             m = m / m.max()
-            pred, target = pred * m, target * m
-        if cfg.with_prior_preservation:
-            pred, pred_prior = torch.chunk(pred, 2, dim=0)
-            target, target_prior = torch.chunk(target, 2, dim=0)
-            loss = (F.mse_loss(pred.float(), target.float(), reduction="none").mean([1, 2, 3]).mean()
-                    + cfg.prior_loss_weight * F.mse_loss(pred_prior.float(), target_prior.float(), reduction="mean"))
-        elif cfg.use_mask:
-            loss = F.mse_loss(pred.float(), target.float(), reduction="none").mean([1, 2, 3]).mean()
+        if fused:
+            from .step_ops import fused_masked_mse
+            w = None
+            if cfg.with_prior_preservation:      # [instance ; class] halves: mean + prior_loss_weight * mean
+                half = bsz // 2
+                w = torch.cat([torch.full((half,), 1.0 / half, device=lat.device),
+                               torch.full((bsz - half,), cfg.prior_loss_weight / (bsz - half), device=lat.device)])
+            loss = fused_masked_mse(pred, target, m, w)
         else:
-            loss = F.mse_loss(pred.float(), target.float(), reduction="mean")
+            if cfg.use_mask:
+                pred, target = pred * m, target * m
+            if cfg.with_prior_preservation:
+                pred, pred_prior = torch.chunk(pred, 2, dim=0)
+                target, target_prior = torch.chunk(target, 2, dim=0)
+                loss = (F.mse_loss(pred.float(), target.float(), reduction="none").mean([1, 2, 3]).mean()
+                        + cfg.prior_loss_weight * F.mse_loss(pred_prior.float(), target_prior.float(), reduction="mean"))
+            elif cfg.use_mask:
+                loss = F.mse_loss(pred.float(), target.float(), reduction="none").mean([1, 2, 3]).mean()
+            else:
+                loss = F.mse_loss(pred.float(), target.float(), reduction="mean")
         from . import ops
         ops.set_side_stream(self._side)
         try:
@@ -307,3 +329,75 @@ class LoraTrainStep:
 
     def d2h_bytes(self) -> int:
         return 4
+
+
+class TextualInversionStep(LoraTrainStep):
+    """Phase 1 of pivotal tuning as a runnable loop: `train_inversion`, cli_lora_pti.py:373-542.
+
+    Per iteration (the reference's order): lr_scheduler.step() FIRST (:417) -> loss_step (:420-431,
+    the same noise / add_noise / text encoder / UNet / (masked) MSE body as the tuning phase, UNet in
+    eval mode, text encoder in train mode) -> backward -> optimizer.step + zero_grad (:447-448) ->
+    norm decay of the placeholder rows (:451-468) -> every other row restored (:477-479).
+    Here only the placeholder rows are trainable (`TextualInversionRows`: a forward hook substitutes
+    them into the embedding lookup, `lb_ti_embed_step` does AdamW + decay + write-back in one
+    kernel), so the 49408 x 768 table is never touched. LoRA factors, if already injected, are
+    frozen for the duration (the reference leaves them requires_grad=True and lets unused gradients
+    pile up; with lora_up = 0 the forward is identical) -- `release()` restores their flags."""
+
+    def __init__(self, unet: nn.Module, text_encoder: nn.Module, placeholder_token_ids, cfg: StepConfig,
+                 lr: float = 5e-4, weight_decay: float = 0.0, clip_ti_decay: bool = True,
+                 latent_shape=(1, 4, 64, 64), seq_len: int = 77, device=None):
+        from .ti import TextualInversionRows
+        self.cfg = cfg
+        self.unet, self.text_encoder = unet, text_encoder
+        self.device = torch.device(device or "cuda")
+        self.noiser = DDPMNoiser(device=self.device)
+        self.model_dtype = next(unet.parameters()).dtype
+        self.latents = torch.zeros(latent_shape, device=self.device, dtype=torch.float32)
+        self.input_ids = torch.zeros((latent_shape[0], seq_len), device=self.device, dtype=torch.long)
+        self.loss = torch.zeros((), device=self.device, dtype=torch.float32)
+        if cfg.external_noise:
+            self.noise = torch.zeros(latent_shape, device=self.device, dtype=torch.float32)
+            self.timesteps = torch.zeros((latent_shape[0],), device=self.device, dtype=torch.long)
+        self.mask = torch.ones((latent_shape[0], 1, latent_shape[2], latent_shape[3]), device=self.device)
+        if cfg.train_inpainting:
+            self.inpaint_mask = torch.zeros((latent_shape[0], 1, latent_shape[2], latent_shape[3]), device=self.device)
+            self.masked_latents = torch.zeros(latent_shape, device=self.device, dtype=torch.float32)
+        self._side = None
+        self._world = 1
+        self.global_step = 0
+        self.graph = self.graph_update = None
+        self.graph_error = None
+        self.base_lr = float(lr)
+        self.ti = TextualInversionRows(text_encoder, placeholder_token_ids, lr=lr, weight_decay=weight_decay,
+                                       clip_ti_decay=clip_ti_decay)
+        self._frozen = []
+        for m in list(unet.modules()) + list(text_encoder.modules()):
+            if type(m).__name__ in ("LoraInjectedLinear", "LoraInjectedConv2d"):
+                for prm in (m.lora_up.weight, m.lora_down.weight):
+                    if prm.requires_grad:
+                        prm.requires_grad_(False)
+                        self._frozen.append(prm)
+        self.unet.eval()               # cli_lora_pti.py:411-412
+        self.text_encoder.train()
+
+    def prepare(self):
+        return None                    # eager loop (phase 1 is not the timed path)
+
+    def step_device(self) -> torch.Tensor:
+        cfg = self.cfg
+        k = self.global_step + 1       # the scheduler is stepped before the update (:417)
+        self.ti.set_lr(self.base_lr * (self.lr_multiplier(k) if cfg.lr_scheduler != "constant" else 1.0))
+        self.global_step += 1
+        if not cfg.train_text_encoder:
+            raise ValueError("TextualInversionStep needs StepConfig.train_text_encoder=True")
+        self._fwd_bwd()                # rows.grad <- d loss / d placeholder rows
+        self.ti.step()                 # AdamW + norm decay + write-back + zero_grad, one kernel
+        return self.loss
+
+    def release(self):
+        """End of phase 1: drop the lookup hook, give the LoRA factors their requires_grad back."""
+        self.ti.remove()
+        for prm in self._frozen:
+            prm.requires_grad_(True)
+        self._frozen = []

@@ -1,7 +1,8 @@
 """Split-K plans of the fused kernels (csrc/fused_core.cuh, SPLITK; planners in fused_linear.cu /
 fused_conv.cu): sites with few output tiles and a long reduction (the dX of the GEGLU projections,
-the 8x8 / 16x16 ResnetBlock2D convs) are split over gridDim.z CTAs per tile, partial accumulators
-travel through an L2-resident fp32 workspace and the last CTA to arrive finishes the tile. Parity
+the 8x8 / 16x16 ResnetBlock2D convs) are split over gridDim.z CTAs per tile, every CTA adds its
+partial accumulator into an L2-resident fp32 buffer (vector reductions) and the last CTA to arrive
+reads the reduced tile back and finishes it. Parity
 against the float64 oracle on exactly the shapes where `auto` picks a split, repeated launches (the
 election counters must reset themselves), CUDA-graph replay, and the dropout drain on a split tile."""
 import pytest
@@ -19,8 +20,8 @@ def rel(a, b):
 
 
 # (M, K, N, r): shapes for which plan_split() chooses split > 1 on a 148-SM part
-LONG_K = [(256, 10240, 1280, 4), (1024, 5120, 640, 8), (64, 10240, 1280, 16), (256, 1280, 1280, 4),
-          (77, 1280, 768, 12), (1, 1280, 320, 8), (200, 2560, 136, 3)]
+LONG_K = [(256, 10240, 1280, 4), (1024, 5120, 640, 8), (64, 10240, 1280, 16), (256, 5120, 1280, 4),
+          (77, 2560, 768, 12), (1, 5120, 320, 8), (200, 2560, 136, 3)]
 
 
 @pytest.mark.parametrize("M,K,N,r", LONG_K)
@@ -52,7 +53,8 @@ def test_split_plan_equals_unsplit_schedule_bitwise_close():
         y_one, t_one, _ = run_fused(x, W, A, B, b, d, 1.0, torch.float32)
     finally:
         _C.lib.lb_debug_set_linear_mode(0)
-    assert rel(t_auto, t_one) < 3e-6 and rel(y_auto, y_one) < 3e-4
+    # fp32 summation order over K = 10240 differs (7 partials reduced at L2 vs one serial chain)
+    assert rel(t_auto, t_one) < 3e-5 and rel(y_auto, y_one) < 3e-4
 
 
 def test_split_plan_inside_a_cuda_graph():
