@@ -257,6 +257,24 @@ int lb_optim_step_fused(float* p, float* g, float* m, float* v, long long n,
                         int n_entries, int max_C, void* shadow16, int shadow_dtype,
                         unsigned int* barrier2, void* stream);
 
+/* lb_optim_step_fused for `world` data-parallel replicas on one NVLink/NVSwitch node, with the
+ * gradient all-reduce INSIDE the launch (no NCCL call; replaces DDP's bucketed all-reduce implied by
+ * accelerator.prepare/backward, train_lora_dreambooth.py:744-757,877): after a flag barrier over
+ * NVLink every rank sums the flat gradient buffers of all ranks by direct peer reads (fixed rank
+ * order => identical sums everywhere), clips on the averaged gradient (DDP order), runs AdamW on its
+ * replica, and zeroes its own gradients once every peer has finished reading them.
+ * peer_g / peer_flags: HOST arrays of `world` device pointers in rank order (the entries of the
+ * other ranks are CUDA-IPC mappings of their `g` / flag buffers; flags = 2*world uint32, zeroed
+ * once); gsum: n floats of scratch; epoch_dev: one zero-initialised uint32. Must be launched by
+ * every rank the same number of times. Waits are bounded (~20 s) and trap. */
+int lb_optim_step_dp(float* p, float* g, float* gsum, float* m, float* v, long long n,
+                     const long long* group_off, int n_groups, const float* lr_dev, float beta1,
+                     float beta2, float eps, float weight_decay, float max_norm, int* step_dev,
+                     float* partials, float* gnorm_out, const long long* table, int n_entries,
+                     int max_C, void* shadow16, int shadow_dtype, unsigned int* barrier2,
+                     const void* const* peer_g, void* const* peer_flags, int world, int rank,
+                     unsigned int* epoch_dev, void* stream);
+
 /* Batched 16-bit shadow refresh after an optimizer step: for every table entry e, j < 16, c < e.C
  *   dst16_base[e.dst_off + j*e.dst_rs + c] = (j < e.r) ? p[e.src_off + j*e.src_rs + c*e.src_cs] : 0
  * table: DEVICE array of n_entries x 7 long long {src_off, src_rs, src_cs, r, C, dst_off, dst_rs}.

@@ -138,6 +138,9 @@ class _FusedLoraConv2dFn(torch.autograd.Function):
 
 
 def lora_conv2d(mod, x):
+    if mod.r > 16:
+        raise LoraB200Error("LoraInjectedConv2d: LoRA rank > 16 is not supported by the fused conv kernel "
+                            "(linear sites run as rank chunks, rank_chunks.py)")
     if mod.training and mod.dropout.p > 0.0:
         from .dropout_path import lora_conv2d_dropout
         return lora_conv2d_dropout(mod, x)

@@ -620,6 +620,167 @@ optim_step_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
   }
 }
 
+// ------------------------------------------------------------------------------- data-parallel optimizer step
+// The gradient all-reduce FUSED into the optimizer step (train_lora_dreambooth.py:744-757,877-888:
+// DDP's bucketed all-reduce, then clip_grad_norm_ + AdamW + zero_grad): one cooperative launch per
+// rank, no NCCL call, so the whole training step is ONE CUDA graph at any world size.
+//   barrier 1 (NVLink flags)  every rank's backward has finished: its flat gradient buffer is final
+//   phase 1   one-shot all-reduce by peer reads: gsum[i] = sum_r g_r[i], r = 0..world-1 in the SAME
+//             order on every rank (bitwise identical sums => replicas stay identical), 16-byte loads
+//             straight from the peers' HBM over NVLink/NVSwitch; per-block partial of gsum^2
+//   grid barrier, then signal barrier 2 ("this rank has finished reading everybody's gradients")
+//   phase 2   clip coefficient (1/world folded in) + AdamW on the local replica from gsum
+//   wait barrier 2, zero the local gradient buffer (peers are done with it)
+//   grid barrier, phase 3: refresh the 16-bit operand shadows
+// Flags: flags[(b * world + r)] in each rank's own memory, b = barrier 0/1, written by rank r with
+// the step's epoch (monotonic, so nothing is ever reset); peers' flag and gradient buffers are
+// CUDA-IPC mappings. Every wait is bounded (~20 s) and traps instead of hanging the box.
+constexpr int DP_MAX_WORLD = 16;
+struct DpPeers {
+  const float* g[DP_MAX_WORLD];       // gradient buffers in rank order (own one included)
+  unsigned int* flags[DP_MAX_WORLD];  // flag arrays in rank order (own one included)
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer16(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// all ranks have written `epoch` into this rank's flags[b*world + r]
+__device__ __forceinline__ void dp_wait_all(const unsigned int* flags, int b, int world, unsigned int epoch) {
+  if (threadIdx.x < world) {
+    const unsigned int* f = flags + b * world + threadIdx.x;
+    const long long t0 = clock64();
+    while (static_cast<int>(ld_acquire_sys(f) - epoch) < 0) {
+      if (clock64() - t0 > 40000000000ll) __trap();
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(OPT_THREADS)
+optim_step_dp_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ gsum,
+                     float* __restrict__ m, float* __restrict__ v, long long n, OptGroups groups,
+                     const float* __restrict__ lr_dev, float beta1, float beta2, float eps, float wd,
+                     float max_norm, int* __restrict__ step_dev, float* __restrict__ partials,
+                     float* __restrict__ gnorm_out, const long long* __restrict__ table, int n_entries,
+                     int max_c, uint16_t* __restrict__ shadow, int fmt, unsigned int* __restrict__ bar,
+                     DpPeers peers, int world, int rank, unsigned int* __restrict__ epoch_dev) {
+  __shared__ float sh[OPT_THREADS / 32];
+  const unsigned int nb = gridDim.x;
+  const unsigned int epoch = epoch_dev[0] + 1u;          // bumped by block 0 at the very end
+  unsigned int* my_flags = peers.flags[rank];
+  const float inv_world = 1.f / static_cast<float>(world);
+  // ---- barrier 1: announce "my gradients are final" to every rank, wait for everybody's
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(peers.flags[threadIdx.x] + 0 * world + rank, epoch);
+  }
+  dp_wait_all(my_flags, 0, world, epoch);
+  // ---- phase 1: gsum = sum over ranks (fixed order), partial sum of squares
+  {
+    float s = 0.f;
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * static_cast<long long>(OPT_THREADS) + threadIdx.x; i < n4;
+         i += static_cast<long long>(nb) * OPT_THREADS) {
+      float4 part[DP_MAX_WORLD];
+#pragma unroll
+      for (int r = 0; r < DP_MAX_WORLD; ++r)
+        if (r < world) part[r] = ld_peer16(peers.g[r] + 4 * i);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < DP_MAX_WORLD; ++r)
+        if (r < world) { a.x += part[r].x; a.y += part[r].y; a.z += part[r].z; a.w += part[r].w; }
+      reinterpret_cast<float4*>(gsum)[i] = a;
+      s += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+      const long long i = (n4 << 2) + threadIdx.x;
+      float a = 0.f;
+      for (int r = 0; r < world; ++r) a += *reinterpret_cast<const volatile float*>(peers.g[r] + i);
+      gsum[i] = a;
+      s += a * a;
+    }
+    const float tot = block_sum(s, sh);
+    if (threadIdx.x == 0) {
+      partials[blockIdx.x] = tot;
+      if (blockIdx.x == 0) step_dev[0] += 1;
+    }
+  }
+  grid_barrier(bar, nb);
+  // ---- barrier 2 (signal only): every block of this rank has finished reading the peers
+  if (blockIdx.x == 0 && threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(peers.flags[threadIdx.x] + 1 * world + rank, epoch);
+  }
+  // ---- phase 2: clip + AdamW from gsum
+  {
+    float s = 0.f;
+    for (unsigned int i = threadIdx.x; i < nb; i += OPT_THREADS) s += __ldcg(partials + i);
+    const float sq = block_sum(s, sh);
+    const float total = sqrtf(sq) * inv_world;
+    float coef = inv_world;
+    if (max_norm > 0.f) coef *= fminf(1.f, max_norm / (total + 1e-6f));
+    if (blockIdx.x == 0 && threadIdx.x == 0 && gnorm_out) gnorm_out[0] = total;
+    const int t = __ldcg(step_dev);
+    const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), static_cast<double>(t)));
+    const float bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), static_cast<double>(t))));
+    for (long long i = blockIdx.x * static_cast<long long>(OPT_THREADS) + threadIdx.x; i < n;
+         i += static_cast<long long>(nb) * OPT_THREADS) {
+      int gi = 0;
+#pragma unroll
+      for (int k = 1; k < OPT_MAX_GROUPS; ++k)
+        if (k < groups.n && i >= groups.off[k]) gi = k;
+      const float lr = lr_dev[gi];
+      const float gg = __ldcg(gsum + i) * coef;
+      float pp = p[i];
+      pp *= (1.f - lr * wd);
+      const float mm = beta1 * m[i] + (1.f - beta1) * gg;
+      const float vv = beta2 * v[i] + (1.f - beta2) * gg * gg;
+      const float denom = sqrtf(vv) / bc2_sqrt + eps;
+      pp -= (lr / bc1) * (mm / denom);
+      p[i] = pp;
+      m[i] = mm;
+      v[i] = vv;
+    }
+  }
+  // ---- peers are done with this rank's gradients: zero them for the next backward pass
+  dp_wait_all(my_flags, 1, world, epoch);
+  for (long long i = blockIdx.x * static_cast<long long>(OPT_THREADS) + threadIdx.x; i < n;
+       i += static_cast<long long>(nb) * OPT_THREADS)
+    g[i] = 0.f;
+  grid_barrier(bar, nb);
+  if (blockIdx.x == 0 && threadIdx.x == 0) epoch_dev[0] = epoch;
+  // ---- phase 3: operand shadows
+  if (n_entries > 0) {
+    const int cblocks = (max_c + OPT_THREADS - 1) / OPT_THREADS;
+    const long long items = static_cast<long long>(n_entries) * cblocks;
+    for (long long it = blockIdx.x; it < items; it += nb) {
+      const int e_i = static_cast<int>(it / cblocks), cb = static_cast<int>(it % cblocks);
+      const long long* e = table + static_cast<size_t>(e_i) * 7;
+      const long long src_off = e[0], rs = e[1], cs = e[2];
+      const int r = static_cast<int>(e[3]), C = static_cast<int>(e[4]);
+      const long long dst_off = e[5], dst_rs = e[6];
+      const int c = cb * OPT_THREADS + threadIdx.x;
+      if (c >= C) continue;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float x = (j < r) ? __ldcg(p + src_off + j * rs + c * cs) : 0.f;
+        shadow[dst_off + j * dst_rs + c] = to16(x, fmt);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------- textual inversion step
 __global__ void bump_step_kernel(int* step_dev) { step_dev[0] += 1; }
 
@@ -1015,5 +1176,56 @@ extern "C" int lb_optim_step_fused(float* p, float* g, float* m, float* v, long 
   cudaError_t e = cudaLaunchKernelEx(&cfg, optim_step_fused_kernel, p, g, m, v, n, groups, lr_dev, beta1, beta2,
                                      eps, weight_decay, max_norm, inv_world, step_dev, partials, gnorm_out,
                                      table, n_entries, max_C, sh, fmt, barrier2);
+  return e == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
+extern "C" int lb_optim_step_dp(float* p, float* g, float* gsum, float* m, float* v, long long n,
+                                const long long* group_off, int n_groups, const float* lr_dev,
+                                float beta1, float beta2, float eps, float weight_decay, float max_norm,
+                                int* step_dev, float* partials, float* gnorm_out, const long long* table,
+                                int n_entries, int max_C, void* shadow16, int shadow_dtype,
+                                unsigned int* barrier2, const void* const* peer_g,
+                                void* const* peer_flags, int world, int rank, unsigned int* epoch_dev,
+                                void* stream) {
+  if (n <= 0 || n_groups < 1 || n_groups > OPT_MAX_GROUPS) return LB_ERR_SHAPE;
+  if (world < 1 || world > DP_MAX_WORLD || rank < 0 || rank >= world) return LB_ERR_SHAPE;
+  if (peer_g == nullptr || peer_flags == nullptr || gsum == nullptr || epoch_dev == nullptr) return LB_ERR_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(gsum)) & 15) return LB_ERR_ALIGN;
+  if (n_entries > 0 && (table == nullptr || shadow16 == nullptr || max_C <= 0)) return LB_ERR_SHAPE;
+  if (n_entries > 0 && shadow_dtype != LB_BF16 && shadow_dtype != LB_F16) return LB_ERR_DTYPE;
+  if (barrier2 == nullptr || partials == nullptr) return LB_ERR_SHAPE;
+  OptGroups groups;
+  groups.n = n_groups;
+  for (int i = 0; i <= n_groups; ++i) groups.off[i] = group_off[i];
+  for (int i = n_groups + 1; i <= OPT_MAX_GROUPS; ++i) groups.off[i] = n;
+  DpPeers peers = {};
+  for (int r = 0; r < world; ++r) {
+    if (peer_g[r] == nullptr || peer_flags[r] == nullptr || (reinterpret_cast<uintptr_t>(peer_g[r]) & 15))
+      return LB_ERR_ALIGN;
+    peers.g[r] = reinterpret_cast<const float*>(peer_g[r]);
+    peers.flags[r] = reinterpret_cast<unsigned int*>(peer_flags[r]);
+  }
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+    return LB_ERR_CUDA;
+  long long want = (n / 4 + OPT_THREADS - 1) / OPT_THREADS;
+  int nblk = static_cast<int>(want < 1 ? 1 : (want > sms ? sms : want));
+  if (nblk > OPT_MAX_PARTIALS) nblk = OPT_MAX_PARTIALS;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(nblk);
+  cfg.blockDim = dim3(OPT_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int fmt = shadow_dtype == LB_BF16;
+  uint16_t* sh = reinterpret_cast<uint16_t*>(shadow16);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, optim_step_dp_kernel, p, g, gsum, m, v, n, groups, lr_dev, beta1,
+                                     beta2, eps, weight_decay, max_norm, step_dev, partials, gnorm_out, table,
+                                     n_entries, max_C, sh, fmt, barrier2, peers, world, rank, epoch_dev);
   return e == cudaSuccess ? LB_OK : LB_ERR_CUDA;
 }

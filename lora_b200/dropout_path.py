@@ -23,8 +23,33 @@ from ._C import LoraB200Error
 from .modules import _LOW, _SiteState, _compute_dtype, _fp32_master, _out_dtype
 
 
+class _SeedPool:
+    """One device-side draw of mask seeds per training step instead of one tiny RNG launch per
+    dropout site (224 sites in the extended SD1.5 set): the step engine calls `begin_step`, every
+    dropout forward takes the next int64 slot (a 1-element view: the kernels read the seed through
+    a device pointer, so a captured graph re-reads freshly drawn values on every replay)."""
+    pool = None
+    used = 0
+
+
+def begin_step(device, n_slots: int = 1024):
+    """Draw this step's mask seeds (graph-capturable: torch's CUDA generator, new values per replay)."""
+    _SeedPool.pool = torch.randint(0, 2 ** 62, (n_slots,), device=device, dtype=torch.int64)
+    _SeedPool.used = 0
+
+
+def end_step():
+    _SeedPool.pool = None
+    _SeedPool.used = 0
+
+
 def _fresh_seed(device) -> torch.Tensor:
-    # drawn on the device from torch's CUDA generator: graph-capturable, new value per replay
+    pool = _SeedPool.pool
+    if pool is not None and pool.device == device and _SeedPool.used < pool.numel():
+        i = _SeedPool.used
+        _SeedPool.used = i + 1
+        return pool[i:i + 1]
+    # no step engine around this call: drawn on the device from torch's CUDA generator
     return torch.randint(0, 2 ** 62, (1,), device=device, dtype=torch.int64)
 
 

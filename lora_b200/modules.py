@@ -303,6 +303,9 @@ class LoraInjectedLinear(nn.Module):
         return torch.diagonal(w.reshape(self.r, self.r)).to(torch.float32).contiguous()
 
     def forward(self, input):
+        if self.r > 16:        # joined LoRAs (lora_manager.py:13-71): rank chunks of 16
+            from .rank_chunks import lora_linear_chunked
+            return lora_linear_chunked(self, input)
         if self.training and self.dropout.p > 0.0:
             from .dropout_path import lora_linear_dropout
             return lora_linear_dropout(self, input)

@@ -131,6 +131,13 @@ class LoraTrainStep:
         cfg = self.cfg
         lat = self.latents
         bsz = lat.shape[0]
+        from . import dropout_path
+        if lat.is_cuda and getattr(self, "_has_dropout", None) is None:
+            self._has_dropout = any(
+                type(m).__name__ in ("LoraInjectedLinear", "LoraInjectedConv2d") and m.dropout.p > 0.0
+                for mod in (self.unet, self.text_encoder) for m in mod.modules())
+        if lat.is_cuda and self._has_dropout:
+            dropout_path.begin_step(lat.device)      # one RNG launch for all dropout sites of the step
         if cfg.external_noise:
             noise, timesteps = self.noise, self.timesteps
         else:
@@ -191,6 +198,7 @@ class LoraTrainStep:
             ops.set_side_stream(None)
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)   # join: all dA/dB are in arena.g
+        dropout_path.end_step()
         self.loss.copy_(loss.detach())
 
     def set_loss_mask(self, mask_image_res: torch.Tensor):

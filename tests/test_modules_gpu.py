@@ -483,3 +483,34 @@ def test_async_wgrad_option_matches_default():
     for a, b in zip(traj[0][0], traj[1][0]):
         assert abs(a - b) < 2e-3 * abs(a)
     assert rel(traj[1][1], traj[0][1]) < 1e-3
+
+
+@pytest.mark.parametrize("r", [32, 20])
+def test_rank_above_16_runs_as_rank_chunks(r):
+    """A lora_join of two rank-16 files is rank 32 (lora_manager.py:13-71): the site must still run
+    (rank chunks of 16, rank_chunks.py) and match the oracle forward and backward, selector included."""
+    import lora_b200 as L
+    from oracle import lora_ops as O
+    torch.manual_seed(r)
+    K, N, M = 320, 640, 300
+    m = L.LoraInjectedLinear(K, N, bias=True, r=r, dropout_p=0.0, scale=0.6).to(DEV)
+    m.linear.requires_grad_(False)
+    m.lora_up.weight.data.normal_(0, 0.05)
+    diag = torch.rand(r, device=DEV) + 0.5
+    m.set_selector_from_diag(diag)
+    x = torch.randn(M, K, device=DEV).to(torch.bfloat16).requires_grad_(True)
+    y = m(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    W16 = m.linear.weight.detach().to(torch.bfloat16)
+    A, B = m.lora_down.weight.detach(), m.lora_up.weight.detach()
+    ref = O.lora_linear_forward(x.detach(), W16, m.linear.bias, A, B, 0.6, diag=diag)
+    base = O.lora_linear_forward(x.detach(), W16, m.linear.bias, A, torch.zeros_like(B), 0.0)
+    branch = float((ref - base).norm())
+    assert float((y.detach().double().cpu() - ref).norm()) <= 2 ** -6 * branch + 2 ** -8 * float(ref.norm())
+    dX, dA, dB = O.lora_linear_backward(gy, x.detach(), W16, A, B, 0.6, diag=diag)
+    assert rel(x.grad, dX) < 2e-2
+    assert rel(m.lora_down.weight.grad, dA) < 2e-2 and rel(m.lora_up.weight.grad, dB) < 2e-2
+    # eval mode / state_dict round trip keep working on the wide site
+    m.eval()
+    assert torch.equal(m(x.detach()), y.detach())
