@@ -304,7 +304,7 @@ def run_native(args):
             m.lora_up.weight.data.normal_(0.0, 0.01, generator=g)
 
     cfg = StepConfig(compute_dtype=dt, use_cuda_graph=not args.no_graph,
-                     capture_collective=args.capture_collective)
+                     capture_collective=args.capture_collective, peer_allreduce=not args.nccl_allreduce)
     seq = 77
     trainer = LoraTrainStep(unet, text, cfg, latent_shape=(1, 4, L_lat, L_lat), seq_len=seq, device=dev)
     vocab = text.config.vocab_size
@@ -397,7 +397,11 @@ def run_native(args):
             "config": bench_config(args, world),
             "engine": {"lora_sites": len(shapes), "lora_params": trainer.arena.n_params,
                        "cuda_graph": trainer.graph is not None, "grouped_launches": not args.no_group,
-                       "graph_error": trainer.graph_error, "loss": loss_dev},
+                       "graph_error": trainer.graph_error, "loss": loss_dev,
+                       "graphs_per_step": (0 if trainer.graph is None else (1 if trainer.graph_update is None else 2)),
+                       "grad_exchange": ("none (1 rank)" if world == 1 else
+                                         ("nvlink peer reads inside lb_optim_step_dp" if trainer.peer_allreduce
+                                          else "nccl all_reduce"))},
             "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": trainer.h2d_bytes(), "d2h_bytes_per_step": trainer.d2h_bytes(),
                     "loss": loss_e2e},
@@ -616,6 +620,8 @@ def main():
     ap.add_argument("--no-group", action="store_true", help="one launch per LoRA site (no grouped launches)")
     ap.add_argument("--capture-collective", action="store_true",
                     help="EXPERIMENTAL: all-reduce inside ONE step graph (thread-local capture mode); run under timeout")
+    ap.add_argument("--nccl-allreduce", action="store_true",
+                    help="N > 1: NCCL all-reduce between two graphs instead of the all-reduce fused into the optimizer launch")
     ap.add_argument("--profile-steps", type=int, default=0, help="run N eager steps and exit (for ncu)")
     ap.add_argument("--roofline-only", action="store_true", help="one eager sweep of the fused kernel (for ncu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -275,6 +275,13 @@ int lb_optim_step_dp(float* p, float* g, float* gsum, float* m, float* v, long l
                      const void* const* peer_g, void* const* peer_flags, int world, int rank,
                      unsigned int* epoch_dev, void* stream);
 
+/* CUDA-IPC helpers for the peer mappings of lb_optim_step_dp. lb_ipc_export: `ptr` (anywhere inside
+ * a cudaMalloc'ed block) -> 64-byte IPC handle of the block + byte offset of ptr inside it.
+ * lb_ipc_open (in another process of the node, once per distinct handle): -> the block's base address
+ * in this process; enables peer access from the current device to the exporter's. */
+int lb_ipc_export(const void* ptr, void* handle64, long long* offset);
+int lb_ipc_open(const void* handle64, void** base_out);
+
 /* Batched 16-bit shadow refresh after an optimizer step: for every table entry e, j < 16, c < e.C
  *   dst16_base[e.dst_off + j*e.dst_rs + c] = (j < e.r) ? p[e.src_off + j*e.src_rs + c*e.src_cs] : 0
  * table: DEVICE array of n_entries x 7 long long {src_off, src_rs, src_cs, r, C, dst_off, dst_rs}.

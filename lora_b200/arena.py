@@ -143,6 +143,55 @@ class LoraArena:
         for s in (s for sg in site_groups for s in sg):
             s._lb.grad_sink = (self._gview(s, "down"), self._gview(s, "up"))
 
+    # ------------------------------------------------------------------ NVLink peer all-reduce
+    def enable_peer_allreduce(self) -> bool:
+        """Map every rank's flat gradient buffer (and a small flag array) into this process over
+        CUDA IPC so that `step()` can run lb_optim_step_dp: the gradient all-reduce happens INSIDE the
+        optimizer launch by direct peer reads over NVLink/NVSwitch -- no NCCL call on the step path,
+        the whole step is capturable as ONE CUDA graph at any world size. All ranks must call this
+        (collectively) and must be on one node. Returns False (and leaves NCCL in place) when the
+        process group is absent / single-rank."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return False
+        world, rank = dist.get_world_size(), dist.get_rank()
+        if world > 16:
+            raise _C.LoraB200Error("enable_peer_allreduce: at most 16 ranks (one NVSwitch node)")
+        dev = self.device
+        self._dp_flags = torch.zeros(2 * world, device=dev, dtype=torch.int32)
+        self._dp_epoch = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.gsum = torch.zeros_like(self.g)
+        torch.cuda.synchronize(dev)
+
+        def export(t):
+            h = ctypes.create_string_buffer(64)
+            off = ctypes.c_longlong(0)
+            check(_C.lib.lb_ipc_export(ptr(t), h, ctypes.byref(off)), "lb_ipc_export")
+            return bytes(h.raw), int(off.value)
+
+        mine = (export(self.g), export(self._dp_flags))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        opened = {}
+
+        def open_(handle, off):
+            if handle not in opened:
+                base = ctypes.c_void_p()
+                check(_C.lib.lb_ipc_open(ctypes.create_string_buffer(handle, 64), ctypes.byref(base)), "lb_ipc_open")
+                opened[handle] = int(base.value)
+            return opened[handle] + off
+
+        g_ptrs, f_ptrs = [], []
+        for r, ((hg, og), (hf, of)) in enumerate(everyone):
+            if r == rank:
+                g_ptrs.append(self.g.data_ptr()); f_ptrs.append(self._dp_flags.data_ptr())
+            else:
+                g_ptrs.append(open_(hg, og)); f_ptrs.append(open_(hf, of))
+        VP = ctypes.c_void_p * world
+        self._dp = (VP(*g_ptrs), VP(*f_ptrs), world, rank)
+        dist.barrier()            # every rank has mapped every buffer before anybody launches
+        return True
+
     def sync_replicas(self, src: int = 0):
         """Broadcast rank `src`'s LoRA factors and optimizer state (p, m, v, Adam's t) to every
         rank; a no-op outside torch.distributed. Called at construction; call it again after
@@ -197,7 +246,10 @@ class LoraArena:
         self.lr.copy_(torch.tensor([float(x) for x in lrs], dtype=torch.float32), non_blocking=True)
 
     def allreduce_grads(self):
-        """The one data-path collective: sum of the flat gradient buffer over NVLink/NVSwitch."""
+        """The one data-path collective: sum of the flat gradient buffer over NVLink/NVSwitch. With
+        enable_peer_allreduce() it is folded into step() (lb_optim_step_dp) and this is a no-op."""
+        if getattr(self, "_dp", None) is not None:
+            return self._dp[2]
         from .dist import allreduce_sum_
         return allreduce_sum_(self.g)
 
@@ -205,6 +257,20 @@ class LoraArena:
              world_size: int = 1):
         """clip_grad_norm_(max_norm) + AdamW + zero_grad on the (already summed) gradients, then the
         16-bit operand shadows -- one cooperative launch (lb_optim_step_fused)."""
+        dp = getattr(self, "_dp", None)
+        if dp is not None:       # all-reduce over NVLink peer memory inside the optimizer launch
+            assert world_size == dp[2], "world size changed after enable_peer_allreduce()"
+            check(_C.lib.lb_optim_step_dp(ptr(self.p), ptr(self.g), ptr(self.gsum), ptr(self.m), ptr(self.v),
+                                          self.n, self._group_off_c, len(self.group_off) - 1, ptr(self.lr),
+                                          beta1, beta2, eps, weight_decay, float(max_norm if max_norm else 0.0),
+                                          ptr(self.step_dev), ptr(self.partials), ptr(self.gnorm),
+                                          ptr(self.table), self.table.shape[0], self.table_max_c,
+                                          ptr(self.shadow), dtype_code(self.compute_dtype), ptr(self._grid_bar),
+                                          dp[0], dp[1], dp[2], dp[3], ptr(self._dp_epoch), stream_ptr()),
+                  "lb_optim_step_dp")
+            ops._count(1)
+            self._publish_shadows()
+            return
         if self.fused_step:
             check(_C.lib.lb_optim_step_fused(ptr(self.p), ptr(self.g), ptr(self.m), ptr(self.v), self.n,
                                              self._group_off_c, len(self.group_off) - 1, ptr(self.lr),

@@ -4,8 +4,10 @@
 //   - global-norm clip + AdamW over the flat LoRA arena  train_lora_dreambooth.py:878-888
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "dropmask.cuh"
 #include "lora_b200.h"
@@ -1177,6 +1179,50 @@ extern "C" int lb_optim_step_fused(float* p, float* g, float* m, float* v, long 
                                      eps, weight_decay, max_norm, inv_world, step_dev, partials, gnorm_out,
                                      table, n_entries, max_C, sh, fmt, barrier2);
   return e == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------- CUDA IPC helpers
+// Peer mappings for lb_optim_step_dp: export a device pointer (any pointer inside a cudaMalloc'ed
+// block, e.g. a slice of a torch caching-allocator segment) as (IPC handle of the block, byte offset
+// inside it); open such a handle in another process of the same node. Opening enables peer access
+// from the current device to the exporting one (cudaIpcMemLazyEnablePeerAccess).
+extern "C" int lb_ipc_export(const void* ptr, void* handle64, long long* offset) {
+  if (ptr == nullptr || handle64 == nullptr || offset == nullptr) return LB_ERR_SHAPE;
+  typedef CUresult (*GetRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static GetRangeFn fn = nullptr;
+  if (fn == nullptr) {
+    void* pfn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &pfn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return LB_ERR_CUDA;
+    fn = reinterpret_cast<GetRangeFn>(pfn);
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, reinterpret_cast<CUdeviceptr>(ptr)) != CUDA_SUCCESS) return LB_ERR_CUDA;
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base)) != cudaSuccess) {
+    cudaGetLastError();
+    return LB_ERR_CUDA;
+  }
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  *offset = static_cast<long long>(reinterpret_cast<CUdeviceptr>(ptr) - base);
+  return LB_OK;
+}
+
+extern "C" int lb_ipc_open(const void* handle64, void** base_out) {
+  if (handle64 == nullptr || base_out == nullptr) return LB_ERR_SHAPE;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+    cudaGetLastError();
+    return LB_ERR_CUDA;
+  }
+  *base_out = p;
+  return LB_OK;
 }
 
 extern "C" int lb_optim_step_dp(float* p, float* g, float* gsum, float* m, float* v, long long n,

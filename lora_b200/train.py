@@ -80,6 +80,11 @@ class StepConfig:
     # the step's prologue (add_noise + cast + channels_last [+ inpainting concat]) and loss epilogue
     # ((masked) MSE + its gradient) as one kernel each (step_ops.py) instead of ~10 small torch ops
     fused_glue: bool = True
+    # data parallel: run the gradient all-reduce INSIDE the optimizer launch over NVLink peer memory
+    # (arena.enable_peer_allreduce / lb_optim_step_dp) -- no NCCL call on the step path, so the whole
+    # step is ONE CUDA graph at any world size. False (or IPC unavailable): one NCCL all-reduce
+    # between two graphs.
+    peer_allreduce: bool = True
 
 
 class LoraTrainStep:
@@ -121,6 +126,19 @@ class LoraTrainStep:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized():
             self._world = dist.get_world_size()
+        self.peer_allreduce = False
+        if self._world > 1 and cfg.peer_allreduce:
+            try:
+                self.peer_allreduce = bool(self.arena.enable_peer_allreduce())
+            except Exception as e:        # e.g. ranks on different nodes: keep the NCCL all-reduce
+                self.peer_allreduce = False
+                self.peer_allreduce_error = f"{type(e).__name__}: {e}"
+            # a rank whose mapping failed must not leave the others waiting on its flags
+            ok = torch.tensor([1.0 if self.peer_allreduce else 0.0], device=self.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok) == 0.0 and self.peer_allreduce:
+                self.peer_allreduce = False
+                self.arena._dp = None
         self.unet.train()
         self.text_encoder.train()
         self._side = torch.cuda.Stream(device=self.device) if cfg.async_wgrad else None
@@ -259,6 +277,14 @@ class LoraTrainStep:
         torch.cuda.synchronize()
 
     def _capture_graphs(self):
+        if self._world == 1 or self.peer_allreduce:
+            # no library collective on the step path (single rank, or the all-reduce lives inside
+            # lb_optim_step_dp): the WHOLE step is one graph
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._body()
+            self.graph, self.graph_update = g, None
+            return
         if self.cfg.capture_collective and self._world > 1:
             import torch.distributed as dist
             dist.barrier()                      # every rank enters its capture at the same time

@@ -53,7 +53,7 @@ def main():
     dev = torch.device("cuda", local)
     os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=dev)
-    cfg = StepConfig(use_cuda_graph=False)
+    cfg = StepConfig(use_cuda_graph=False, peer_allreduce=os.environ.get("LB_DP_NCCL", "0") != "1")
     # (a) distributed: each rank one sample
     unet, text = build(dev)
     tr = LoraTrainStep(unet, text, cfg, latent_shape=(1, 4, 16, 16), device=dev)
@@ -65,7 +65,8 @@ def main():
     p_dist = tr.arena.p.clone()
     # (b) single process emulation on every rank: accumulate all N samples, inv_world = 1/N
     unet2, text2 = build(dev)
-    tr2 = LoraTrainStep(unet2, text2, cfg, latent_shape=(1, 4, 16, 16), device=dev)
+    cfg2 = StepConfig(use_cuda_graph=False, peer_allreduce=False)     # local emulation: no exchange at all
+    tr2 = LoraTrainStep(unet2, text2, cfg2, latent_shape=(1, 4, 16, 16), device=dev)
     tr2._world = 1
     for step in range(3):
         for r in range(world):
@@ -80,7 +81,8 @@ def main():
     flags = torch.tensor([err, 0.0 if same else 1.0], device=dev)
     dist.all_reduce(flags, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"dp_parity world={world} rel_err_vs_single_process={float(flags[0]):.3e} replicas_identical={float(flags[1]) == 0.0}")
+        print(f"dp_parity world={world} exchange={'nvlink-peer (lb_optim_step_dp)' if tr.peer_allreduce else 'nccl'} "
+              f"rel_err_vs_single_process={float(flags[0]):.3e} replicas_identical={float(flags[1]) == 0.0}")
         assert float(flags[0]) < 5e-3 and float(flags[1]) == 0.0
         print("dp_parity OK")
     dist.destroy_process_group()
