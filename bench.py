@@ -236,6 +236,66 @@ def roofline_sweep(trainer, families, iters=10, eager_once=False):
     return total_bytes, ms, len(launches)
 
 
+def conv_bytes(n, cin, cout, k, H, W, r, e=2):
+    """a conv site counts the activation ONCE (not im2col-expanded): X + W + down + Y
+    (16-bit) + up (fp32) + bias (fp32) + T [pixels,16] fp32."""
+    P, taps = n * H * W, k * k
+    return e * (P * cin + cout * taps * cin + r * taps * cin + P * cout) + 4 * cout * r + 4 * cout + 4 * P * 16
+
+
+def conv_sweep(trainer, conv_sites, iters=10):
+    """Every fused LoRA-conv launch of one extended step: forward (dropout mask fused into the drain,
+    the configs[2] default p = 0.1) and the input gradient (per-tap T groups), real ResnetBlock2D
+    shapes, private buffers, one CUDA graph, CUDA-event timed."""
+    from lora_b200 import ops
+    dev, dt = trainer.device, trainer.cfg.compute_dtype
+    seed = torch.zeros(1, device=dev, dtype=torch.int64)
+    launches, total = [], 0
+    for (n, cin, cout, k, H, W, r) in conv_sites:
+        taps, pad = k * k, k // 2
+        x = torch.randn(n, cin, H, W, device=dev, dtype=dt).contiguous(memory_format=torch.channels_last)
+        gy = torch.randn(n, cout, H, W, device=dev, dtype=dt).contiguous(memory_format=torch.channels_last)
+        w = torch.randn(cout, cin, k, k, device=dev) * 0.02
+        wf, wb = ops.cast_conv_weight(w, dt, True, True)
+        A = torch.randn(r, cin, k, k, device=dev)
+        B = torch.randn(cout, r, device=dev) * 0.01
+        d16 = ops.conv_down16(A, dt, {})
+        bt16 = ops.cast_rows_pad16(B, 1, r, r, cout, dt)
+        bias = torch.zeros(cout, device=dev)
+        A32 = A.contiguous()
+        launches.append(lambda x=x, wf=wf, bias=bias, d16=d16, B=B, r=r, cout=cout, k=k, pad=pad:
+                        ops.fused_conv2d(x, wf, bias, d16, B, 0, r, 1, 0, None, 1.0, r, cout, k, k, pad, pad, False,
+                                         dt, True, drop_p=0.1, seed=seed))
+        launches.append(lambda gy=gy, wb=wb, bt16=bt16, A32=A32, r=r, cin=cin, k=k, pad=pad, taps=taps:
+                        ops.fused_conv2d(gy, wb, None, bt16, A32, taps - 1, taps, cin * taps, -1, None, 1.0, r, cin,
+                                         k, k, k - 1 - pad, k - 1 - pad, True, dt, True))
+        total += conv_bytes(n, cin, cout, k, H, W, r) + conv_bytes(n, cout, cin, k, H, W, r)
+
+    def run():
+        for f in launches:
+            f()
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run(); run()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        run()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return total, e0.elapsed_time(e1) / iters, len(launches)
+
+
 def record_tokens(unet, text):
     """Forward hooks: rows (tokens) seen by each LoRA linear in one step."""
     seen = {}
@@ -317,6 +377,14 @@ def run_native(args):
     if not args.no_group:
         L.set_grouping(True)             # q/k/v-type sites that share an input: one launch per family
     seen, hooks = record_tokens(unet, text)
+    conv_seen = {}
+    if args.extended:
+        for m in unet.modules():
+            if type(m).__name__ == "LoraInjectedConv2d":
+                hooks.append(m.register_forward_pre_hook(
+                    lambda mod, inp: conv_seen.__setitem__(id(mod), (inp[0].shape[0], mod.conv.in_channels,
+                                                                     mod.conv.out_channels, mod.conv.kernel_size[0],
+                                                                     inp[0].shape[2], inp[0].shape[3], mod.r))))
     trainer._body()                      # eager step 1: records tokens per site, learns site families
     ops.LAUNCH_COUNT = 0
     trainer._body()                      # eager step 2: the steady-state launch count
@@ -389,6 +457,16 @@ def run_native(args):
             with open(tpath) as fh:
                 traffic = json.load(fh).get("dram_bytes_per_sweep")
         value = world * args.steps / (ms_dev * 1e-3)
+        conv_roof = None
+        if args.extended and conv_seen:
+            cb, cms, cn = conv_sweep(trainer, list(conv_seen.values()))
+            c_ach = cb / (cms * 1e-3) / 1e9
+            conv_roof = {"bound": "hbm", "kernel": "fused_lora_kernel<CONV>: forward (dropout fused in the drain) + input "
+                         "gradient (per-tap T groups) of every LoRA conv site of one extended step",
+                         "sites": 2 * len(conv_seen), "achieved": c_ach, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": c_ach / hbm_peak, "launches": cn, "algorithmic_bytes": cb, "ms_per_sweep": cms,
+                         "avg_launch_us": cms * 1e3 / cn, "share_of_step": cms / (ms_dev / args.steps),
+                         "peak_source": peak_src}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps,
@@ -416,6 +494,8 @@ def run_native(args):
                          "avg_launch_us": rms * 1e3 / n_l,
                          "share_of_step": rms / (ms_dev / args.steps), "peak_source": peak_src},
         }
+        if conv_roof is not None:
+            out["roofline_conv"] = conv_roof
         if world == 1 and not args.no_cuda_baseline:
             # the reference's operator modules (oracle port) in the same host models on THIS GPU:
             # torch eager (what the reference runs) and, generously, the same step graph-replayed

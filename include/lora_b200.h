@@ -118,6 +118,25 @@ int lb_lora_wgrad_pair(const void* X, const float* dTs, float* dA, long long dA_
                        long long dB_cs, int N, const float* diag, float scale, int M, int r,
                        float drop_p, const void* seed_dev, int in_dtype, void* stream);
 
+/* One reduction  out[j*out_js + c*out_cs] += scale*diag[j] * sum_{m<M} V[m,j] * S[m,c]  (see
+ * lb_lora_wgrad; drop_p > 0: S masked like lb_lora_wgrad_masked with the uint64 at seed_dev). */
+typedef struct lb_wgrad_problem {
+  const void* S;        /* [M, C] rows of in_dtype                         */
+  const float* V;       /* [M, 16] fp32                                    */
+  float* out;
+  long long out_js, out_cs;
+  int M, C, r;
+  float scale;
+  const float* diag;    /* selector diagonal [r] or NULL                   */
+  float drop_p;
+  const void* seed_dev; /* device uint64 (drop_p > 0) or NULL              */
+} lb_wgrad_problem;
+
+/* n independent reductions (HOST array) in ceil(n/24) launches. The step engine queues the dA / dB
+ * of every linear site during backward and flushes them here once: the factor gradients feed only
+ * the optimizer (autograd's dA/dB GEMMs of lora.py:53-58 for all sites at once). */
+int lb_lora_wgrad_batch(const lb_wgrad_problem* probs, int n, int in_dtype, void* stream);
+
 /* lb_lora_wgrad_pair for up to 4 sites that share X (a grouped family), one launch; HOST arrays. */
 int lb_lora_wgrad_multi(int n, const void* X, const float* const* dTs, float* const* dA,
                         const void* const* gY, const float* const* T, float* const* dB, const int* N,

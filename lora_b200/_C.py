@@ -60,6 +60,7 @@ def _load():
                               vp, vp, vp, vp, i32, i32, vp, i32, vp, vp, vp, i32, i32, vp, vp], i32),
         "lb_ipc_export": ([vp, vp, ctypes.POINTER(ll)], i32),
         "lb_ipc_open": ([vp, ctypes.POINTER(vp)], i32),
+        "lb_lora_wgrad_batch": ([vp, i32, i32, vp], i32),
         "lb_refresh_shadows": ([vp, vp, i32, i32, vp, i32, vp], i32),
         "lb_debug_set_linear_mode": ([i32], i32),
         "lb_lora_wgrad_conv": ([vp, vp, vp, f32, vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp], i32),
@@ -128,7 +129,7 @@ EXPORTED = [n for n in ("lb_abi_version", "lb_lora_linear_fwd", "lb_lora_wgrad",
                         "lb_svd_chol_inv", "lb_svd_apply", "lb_svd_jacobi", "lb_svd_randn", "lb_split_bf16x3", "lb_lora_merge", "lb_ti_embed_step", "lb_lora_linear_fwd_grouped", "lb_lora_wgrad_multi", "lb_lora_wgrad_conv",
                         "lb_lora_linear_fwd_dropout", "lb_lora_conv2d_fwd_dropout", "lb_debug_set_pdl", "lb_svd_workspace_bytes", "lb_svd_truncated_batched",
                         "lb_optim_step_fused", "lb_step_prologue", "lb_masked_mse_fwd_bwd",
-                        "lb_optim_step_dp", "lb_ipc_export", "lb_ipc_open")]
+                        "lb_optim_step_dp", "lb_ipc_export", "lb_ipc_open", "lb_lora_wgrad_batch")]
 
 
 def check(status: int, what: str):

@@ -130,7 +130,8 @@ class _FusedLoraConv2dFn(torch.autograd.Function):
         if need_b:
             tgt = sink[1] if sink is not None else torch.zeros((cout, r), device=gy.device,
                                                                dtype=torch.float32)
-            ops.wgrad_shift(gy16, T, ctx.diag, ctx.scale, tgt, 0, 1, r, r, cout, 0, 0, 0, 0)
+            gy2d = gy16.permute(0, 2, 3, 1).reshape(n * h * w, cout)       # NHWC bytes as [pixels, Cout]
+            ops.wgrad(gy2d, T, ctx.diag, ctx.scale, tgt, 1, r, r, async_ok=sink is not None)
             if sink is None:
                 dB = tgt.view_as(B).to(B.dtype)
         dx = dX.to(ctx.x_dtype) if need_x else None

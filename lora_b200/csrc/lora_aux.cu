@@ -57,10 +57,12 @@ struct WgProblem {
   const float* diag;   // selector diagonal of this problem's site (or null)
   float scale;
   int r;
+  int M;               // rows of this problem (0: the launch-wide WgArgs::M)
+  const unsigned long long* seed;  // mask seed of this problem (null: the launch-wide seed_dev)
 };
-constexpr int WG_MAXP = 8;
+constexpr int WG_MAXP = 24;
 struct WgArgs {
-  WgProblem pr[WG_MAXP];  // dA and dB of up to 4 sites share a launch
+  WgProblem pr[WG_MAXP];  // dA / dB of several sites share a launch (lb_lora_wgrad_batch: up to 24)
   int nb_start[WG_MAXP + 1];  // prefix sum of 128-column blocks per problem
   int n_pr;
   const unsigned long long* seed_dev;
@@ -96,14 +98,16 @@ wgrad_kernel(const WgArgs a) {
 #pragma unroll
   for (int j = 0; j < RQ * 4; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
   const float drop_p = P.drop_p;
-  const unsigned long long sd = (drop_p > 0.f) ? a.seed_dev[0] : 0ull;
+  const int PM = P.M > 0 ? P.M : a.M;                 // rows of THIS problem
+  if (static_cast<long long>(blockIdx.y) * a.slabs * WG_ROWS >= PM) return;   // batch: shorter problem
+  const unsigned long long sd = (drop_p > 0.f) ? (P.seed ? P.seed[0] : a.seed_dev[0]) : 0ull;
   const float inv = (drop_p > 0.f) ? 1.f / (1.f - drop_p) : 1.f;
 
   auto load_rows = [&](int m_base, uint4 (&raw)[WG_RPW]) {
 #pragma unroll
     for (int i = 0; i < WG_RPW; ++i) {
       const int m = m_base + i;
-      bool ok = col_ok && m < a.M;
+      bool ok = col_ok && m < PM;
       long long src = m;
       if (cH > 0 && ok) {
         // conv weight-gradient tap: row m is pixel (h, w) of an NHWC image; S is read at the pixel
@@ -128,12 +132,12 @@ wgrad_kernel(const WgArgs a) {
   load_rows(m_first, cur);
   for (int sl = 0; sl < a.slabs; ++sl) {
     const int m_base = m_first + sl * WG_ROWS;
-    if (m_base >= a.M) break;
+    if (m_base >= PM) break;
     if (sl + 1 < a.slabs) load_rows(m_base + WG_ROWS, nxt);   // next slab's rows in flight
 #pragma unroll
     for (int i = 0; i < WG_RPW; ++i) {
       const int m = m_base + i;
-      if (m < a.M) {
+      if (m < PM) {
         float x[4];
         if (f32in) {
           x[0] = __uint_as_float(cur[i].x); x[1] = __uint_as_float(cur[i].y);
@@ -603,20 +607,18 @@ optim_step_fused_kernel(float* __restrict__ p, float* __restrict__ g, float* __r
   grid_barrier(bar, nb);
   // ---- phase 3: work item = (table entry, 256-column block); p is read through L2 (just written)
   {
-    const int cblocks = (max_c + OPT_THREADS - 1) / OPT_THREADS;
-    const long long items = static_cast<long long>(n_entries) * cblocks;
-    for (long long it = blockIdx.x; it < items; it += nb) {
-      const int e_i = static_cast<int>(it / cblocks), cb = static_cast<int>(it % cblocks);
+    // one table entry per block iteration (entries have 64 ... 10240 columns: no empty work items)
+    for (int e_i = blockIdx.x; e_i < n_entries; e_i += nb) {
       const long long* e = table + static_cast<size_t>(e_i) * 7;
-      const long long src_off = e[0], rs = e[1], cs = e[2];
-      const int r = static_cast<int>(e[3]), C = static_cast<int>(e[4]);
-      const long long dst_off = e[5], dst_rs = e[6];
-      const int c = cb * OPT_THREADS + threadIdx.x;
-      if (c >= C) continue;
+      const long long src_off = __ldg(e), rs = __ldg(e + 1), cs = __ldg(e + 2);
+      const int r = static_cast<int>(__ldg(e + 3)), C = static_cast<int>(__ldg(e + 4));
+      const long long dst_off = __ldg(e + 5), dst_rs = __ldg(e + 6);
+      for (int c = threadIdx.x; c < C; c += OPT_THREADS) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float x = (j < r) ? __ldcg(p + src_off + j * rs + c * cs) : 0.f;
-        shadow[dst_off + j * dst_rs + c] = to16(x, fmt);
+        for (int j = 0; j < 16; ++j) {
+          const float x = (j < r) ? __ldcg(p + src_off + j * rs + c * cs) : 0.f;
+          shadow[dst_off + j * dst_rs + c] = to16(x, fmt);
+        }
       }
     }
   }
@@ -764,20 +766,18 @@ optim_step_dp_kernel(float* __restrict__ p, float* __restrict__ g, float* __rest
   if (blockIdx.x == 0 && threadIdx.x == 0) epoch_dev[0] = epoch;
   // ---- phase 3: operand shadows
   if (n_entries > 0) {
-    const int cblocks = (max_c + OPT_THREADS - 1) / OPT_THREADS;
-    const long long items = static_cast<long long>(n_entries) * cblocks;
-    for (long long it = blockIdx.x; it < items; it += nb) {
-      const int e_i = static_cast<int>(it / cblocks), cb = static_cast<int>(it % cblocks);
+    // one table entry per block iteration (entries have 64 ... 10240 columns: no empty work items)
+    for (int e_i = blockIdx.x; e_i < n_entries; e_i += nb) {
       const long long* e = table + static_cast<size_t>(e_i) * 7;
-      const long long src_off = e[0], rs = e[1], cs = e[2];
-      const int r = static_cast<int>(e[3]), C = static_cast<int>(e[4]);
-      const long long dst_off = e[5], dst_rs = e[6];
-      const int c = cb * OPT_THREADS + threadIdx.x;
-      if (c >= C) continue;
+      const long long src_off = __ldg(e), rs = __ldg(e + 1), cs = __ldg(e + 2);
+      const int r = static_cast<int>(__ldg(e + 3)), C = static_cast<int>(__ldg(e + 4));
+      const long long dst_off = __ldg(e + 5), dst_rs = __ldg(e + 6);
+      for (int c = threadIdx.x; c < C; c += OPT_THREADS) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float x = (j < r) ? __ldcg(p + src_off + j * rs + c * cs) : 0.f;
-        shadow[dst_off + j * dst_rs + c] = to16(x, fmt);
+        for (int j = 0; j < 16; ++j) {
+          const float x = (j < r) ? __ldcg(p + src_off + j * rs + c * cs) : 0.f;
+          shadow[dst_off + j * dst_rs + c] = to16(x, fmt);
+        }
       }
     }
   }
@@ -977,6 +977,34 @@ extern "C" int lb_lora_wgrad_multi(int n, const void* X, const float* const* dTs
   a.n_pr = 2 * n;
   a.M = M;
   return wgrad_run(a, in_dtype, stream);
+}
+
+// Many independent reductions out[j,c] += scale*diag[j] * sum_m V[m,j] S[m,c] in as few launches as
+// possible (24 problems per launch): the dA / dB of EVERY linear site of a step, queued during
+// backward and flushed once at its end -- they feed only the optimizer, and one launch over
+// hundreds of MB fills the chip where 120-270 launches over a few MB each were latency-bound.
+extern "C" int lb_lora_wgrad_batch(const lb_wgrad_problem* probs, int n, int in_dtype, void* stream) {
+  if (probs == nullptr || n < 1) return LB_ERR_SHAPE;
+  for (int base = 0; base < n; base += WG_MAXP) {
+    const int cnt = (n - base) < WG_MAXP ? (n - base) : WG_MAXP;
+    WgArgs a = {};
+    int max_m = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const lb_wgrad_problem& q = probs[base + i];
+      if (q.M <= 0 || !(q.drop_p >= 0.f && q.drop_p < 1.f) || (q.drop_p > 0.f && q.seed_dev == nullptr))
+        return LB_ERR_SHAPE;
+      WgProblem& w = a.pr[i];
+      w.S = reinterpret_cast<const uint2*>(q.S); w.V = q.V; w.out = q.out; w.js = q.out_js; w.cs = q.out_cs;
+      w.C = q.C; w.drop_p = q.drop_p; w.diag = q.diag; w.scale = q.scale; w.r = q.r; w.M = q.M;
+      w.seed = reinterpret_cast<const unsigned long long*>(q.seed_dev);
+      max_m = q.M > max_m ? q.M : max_m;
+    }
+    a.n_pr = cnt;
+    a.M = max_m;
+    const int rc = wgrad_run(a, in_dtype, stream);
+    if (rc != LB_OK) return rc;
+  }
+  return LB_OK;
 }
 
 extern "C" int lb_lora_up_dropout(void* Y, int y_dtype, const float* T, const float* up,

@@ -107,11 +107,11 @@ class _LoraLinearDropoutFn(torch.autograd.Function):
         if need_b:
             tB = sink[1] if sink is not None else torch.zeros((N, r), device=gy.device, dtype=torch.float32)
         if need_a and need_b:
-            ops.wgrad_pair(x2d, dTs, tA, gy2d, T, tB, ctx.diag, ctx.scale, r, ctx.p, seed)
+            ops.wgrad_pair(x2d, dTs, tA, gy2d, T, tB, ctx.diag, ctx.scale, r, ctx.p, seed, async_ok=sink is not None)
         elif need_a:
-            ops.wgrad(x2d, dTs, ctx.diag, ctx.scale, tA, K, 1, r)
+            ops.wgrad(x2d, dTs, ctx.diag, ctx.scale, tA, K, 1, r, async_ok=sink is not None)
         elif need_b:
-            ops.wgrad_masked(gy2d, T, ctx.diag, ctx.scale, tB, 1, r, r, ctx.p, seed)
+            ops.wgrad_masked(gy2d, T, ctx.diag, ctx.scale, tB, 1, r, r, ctx.p, seed, async_ok=sink is not None)
         if sink is None:
             dA = tA.to(A.dtype).view_as(A) if need_a else None
             dB = tB.to(B.dtype).view_as(B) if need_b else None
@@ -183,7 +183,7 @@ class _LoraConv2dDropoutFn(torch.autograd.Function):
                 dA = tgt.view_as(A).to(A.dtype)
         if need_b:
             tgt = sink[1] if sink is not None else torch.zeros((cout, r), device=gy.device, dtype=torch.float32)
-            ops.wgrad_masked(gy2d, T, ctx.diag, ctx.scale, tgt, 1, r, r, ctx.p, seed)
+            ops.wgrad_masked(gy2d, T, ctx.diag, ctx.scale, tgt, 1, r, r, ctx.p, seed, async_ok=sink is not None)
             if sink is None:
                 dB = tgt.view_as(B).to(B.dtype)
         dx = dX.to(ctx.x_dtype) if need_x else None

@@ -31,6 +31,55 @@ def set_side_stream(stream):
     _SIDE = stream
 
 
+# Deferred factor gradients: dA / dB feed only the optimizer, so (when they accumulate straight into
+# an arena) a step engine can QUEUE every linear-site reduction of the backward pass and run them
+# all in ceil(n/24) launches at its end (lb_lora_wgrad_batch) instead of one small launch per site.
+# The queue keeps the operand tensors alive until the flush.
+import ctypes as _ct
+
+
+class _WgProblemC(_ct.Structure):
+    _fields_ = [("S", _ct.c_void_p), ("V", _ct.c_void_p), ("out", _ct.c_void_p),
+                ("out_js", _ct.c_longlong), ("out_cs", _ct.c_longlong),
+                ("M", _ct.c_int), ("C", _ct.c_int), ("r", _ct.c_int), ("scale", _ct.c_float),
+                ("diag", _ct.c_void_p), ("drop_p", _ct.c_float), ("seed_dev", _ct.c_void_p)]
+
+
+_WG_QUEUE = None      # None: launch immediately; dict dtype -> [(_WgProblemC fields, keepalive)]
+
+
+def wgrad_defer_begin():
+    global _WG_QUEUE
+    _WG_QUEUE = {}
+
+
+def wgrad_defer_cancel():
+    global _WG_QUEUE
+    _WG_QUEUE = None
+
+
+def _wgrad_enqueue(S, V, out, out_js, out_cs, M, C, r, scale, diag, drop_p=0.0, seed=None):
+    dp = lambda t: None if t is None else t.data_ptr()
+    item = (dp(S), dp(V), dp(out), int(out_js), int(out_cs), int(M), int(C), int(r), float(scale), dp(diag),
+            float(drop_p), dp(seed))
+    _WG_QUEUE.setdefault(S.dtype, []).append((item, (S, V, out, diag, seed)))
+
+
+def wgrad_flush():
+    """Run every queued reduction (lb_lora_wgrad_batch) and leave deferral mode."""
+    global _WG_QUEUE
+    q, _WG_QUEUE = _WG_QUEUE, None
+    if not q:
+        return 0
+    n_launch = 0
+    for dtype, items in q.items():
+        arr = (_WgProblemC * len(items))(*[_WgProblemC(*it[0]) for it in items])
+        check(_C.lib.lb_lora_wgrad_batch(arr, len(items), dtype_code(dtype), stream_ptr()), "lb_lora_wgrad_batch")
+        n_launch += (len(items) + 23) // 24
+    _count(n_launch)
+    return n_launch
+
+
 def _maybe_side(async_ok: bool, tensors, fn):
     if _SIDE is None or not async_ok:
         fn()
@@ -117,6 +166,9 @@ def wgrad(S: torch.Tensor, V: torch.Tensor, diag: Optional[torch.Tensor], scale:
     M, C = S.shape
     assert S.is_contiguous() and V.shape == (M, R_PAD) and V.dtype == torch.float32
     assert out.dtype == torch.float32
+    if _WG_QUEUE is not None and async_ok:
+        _wgrad_enqueue(S, V, out, out_js, out_cs, M, C, r, scale, diag)
+        return
     _maybe_side(async_ok, (S, V, diag), lambda: check(
         _C.lib.lb_lora_wgrad(ptr(S), ptr(V), ptr(diag), float(scale), ptr(out), out_js, out_cs,
                              M, C, r, dtype_code(S.dtype), stream_ptr()), "lb_lora_wgrad"))
@@ -238,9 +290,12 @@ def dropout_dt(gy2d: torch.Tensor, up: torch.Tensor, up_rs: int, up_cs: int, p: 
 
 
 def wgrad_masked(S: torch.Tensor, V: torch.Tensor, diag, scale: float, out: torch.Tensor,
-                 out_js: int, out_cs: int, r: int, p: float, seed: torch.Tensor):
+                 out_js: int, out_cs: int, r: int, p: float, seed: torch.Tensor, async_ok: bool = False):
     _req_cuda(S, V, out, seed)
     M, C = S.shape
+    if _WG_QUEUE is not None and async_ok:
+        _wgrad_enqueue(S, V, out, out_js, out_cs, M, C, r, scale, diag, p, seed)
+        return
     check(_C.lib.lb_lora_wgrad_masked(ptr(S), ptr(V), ptr(diag), float(scale), ptr(out), out_js,
                                       out_cs, M, C, r, float(p), ptr(seed), dtype_code(S.dtype),
                                       stream_ptr()), "lb_lora_wgrad_masked")
@@ -255,6 +310,10 @@ def wgrad_pair(x2d: torch.Tensor, dTs: torch.Tensor, dA: torch.Tensor, gy2d: tor
     M, K = x2d.shape
     N = gy2d.shape[1]
     assert gy2d.shape[0] == M and dA.dtype == torch.float32 and dB.dtype == torch.float32
+    if _WG_QUEUE is not None and async_ok:
+        _wgrad_enqueue(x2d, dTs, dA, K, 1, M, K, r, scale, diag)
+        _wgrad_enqueue(gy2d, T, dB, 1, r, M, N, r, scale, diag, p, seed)
+        return
     _maybe_side(async_ok, (x2d, dTs, gy2d, T, diag, seed), lambda: check(
         _C.lib.lb_lora_wgrad_pair(ptr(x2d), ptr(dTs), ptr(dA), K, 1, K, ptr(gy2d), ptr(T), ptr(dB),
                                   1, r, N, ptr(diag), float(scale), M, r, float(p), ptr(seed),
@@ -322,6 +381,11 @@ def wgrad_multi(x2d: torch.Tensor, items, async_ok: bool = False):
     n = len(items)
     VP, I, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     M, K = x2d.shape
+    if _WG_QUEUE is not None and async_ok:
+        for (dTs, dA, gy2d, T, dB, diag, scale, r) in items:
+            _wgrad_enqueue(x2d, dTs, dA, K, 1, M, K, r, scale, diag)
+            _wgrad_enqueue(gy2d, T, dB, 1, r, M, gy2d.shape[1], r, scale, diag)
+        return
     dp = lambda t: None if t is None else t.data_ptr()
     arr = lambda ty, vals: (ty * n)(*vals)
     a = (arr(VP, [it[0].data_ptr() for it in items]), arr(VP, [it[1].data_ptr() for it in items]),

@@ -85,6 +85,9 @@ class StepConfig:
     # step is ONE CUDA graph at any world size. False (or IPC unavailable): one NCCL all-reduce
     # between two graphs.
     peer_allreduce: bool = True
+    # queue the dA / dB reductions of all linear sites (and the conv sites' dB) during backward and
+    # run them in ceil(n/24) launches at its end (ops.wgrad_flush / lb_lora_wgrad_batch)
+    defer_wgrad: bool = True
 
 
 class LoraTrainStep:
@@ -210,10 +213,18 @@ class LoraTrainStep:
                 loss = F.mse_loss(pred.float(), target.float(), reduction="mean")
         from . import ops
         ops.set_side_stream(self._side)
+        import os as _os
+        defer = (cfg.defer_wgrad and self._side is None and lat.is_cuda and hasattr(self, "arena")
+                 and _os.environ.get("LB_NO_DEFER", "0") != "1")
+        if defer:
+            ops.wgrad_defer_begin()
         try:
             loss.backward()
+            if defer:
+                ops.wgrad_flush()
         finally:
             ops.set_side_stream(None)
+            ops.wgrad_defer_cancel()
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)   # join: all dA/dB are in arena.g
         dropout_path.end_step()
