@@ -391,3 +391,39 @@ def test_lr_step_first_selects_the_pti_schedule_order():
         assert all(abs(a - b) < 1e-18 for got, w in zip(tr.arena.seen, want) for a, b in zip(got, w))
         if first:       # exactly what the reference loop used
             assert all(abs(a - b) < 1e-12 for got, st in zip(tr.arena.seen, G["steps"]) for a, b in zip(got, st["lrs"]))
+
+
+def test_latent_cache_restates_cached_latents_branch():
+    """cli_lora_pti.py:141-151: latents = vae.encode(image).latent_dist.sample() * 0.18215, once per item."""
+    from lora_b200.step_ops import LatentCache
+
+    class _Dist:
+        def __init__(self, x):
+            self.x = x
+
+        def sample(self):
+            return self.x[:, :4, ::8, ::8] * 2.0
+
+    class _Enc:
+        def __init__(self, x):
+            self.latent_dist = _Dist(x)
+
+    class _VAE(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.zeros(1))
+            self.calls = 0
+
+        def encode(self, x):
+            self.calls += 1
+            return _Enc(x)
+
+    vae = _VAE()
+    data = [{"instance_images": torch.randn(4, 64, 64), "instance_prompt_ids": torch.tensor([1, 2, 3])} for _ in range(3)]
+    cache = LatentCache().build(vae, data)
+    assert len(cache) == 3 and vae.calls == 3
+    for item, src in zip(cache.items, data):
+        assert item["instance_images"].shape == (4, 8, 8)
+        assert torch.allclose(item["instance_images"], src["instance_images"][:4, ::8, ::8] * 2.0 * 0.18215)
+        assert torch.equal(item["instance_prompt_ids"], src["instance_prompt_ids"])
+    assert data[0]["instance_images"].shape == (4, 64, 64)          # the dataset itself is not modified
