@@ -43,6 +43,11 @@ def bench_config(args, world, lora_sites=None, lora_params=None):
     elif args.extended:
         wl = ("SD1.5 --use_extended_lora (ResBlock Conv2d LoRA, dropout 0.1) UNet+text_encoder 512x512 bf16 "
               "bs=1/GPU (configs[2] shape)")
+    elif args.res == 768 and args.rank == 16:
+        wl = ("SD1.5 UNet+text_encoder LoRA rank=16 768x768 bf16 bs=1/GPU LoRA-tuning step of cli_lora_pti "
+              "(configs[3] shape)")
+    elif args.res != 512 or args.rank != 4:
+        wl = f"SD1.5 UNet+text_encoder LoRA rank={args.rank} {args.res}x{args.res} bf16 bs=1/GPU dreambooth step"
     else:
         wl = WORKLOAD
     return {"workload": wl, "extended": bool(args.extended), "resolution": args.res, "rank": args.rank,
@@ -325,17 +330,15 @@ def run_native(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # An externally set NCCL_DEBUG (the driver's communicator check reads NCCL's INFO lines) is
-        # honoured and NCCL's output is left where NCCL puts it. Only when nobody asked for NCCL
-        # logging do we default to WARN and keep NCCL's version banner (printed to STDOUT at
-        # communicator creation) off stdout by parking fd 1 on stderr while the communicator is built.
-        external_nccl_debug = "NCCL_DEBUG" in os.environ
-        if not external_nccl_debug:
+        # honoured as is; only when nobody asked for NCCL logging do we default to WARN. In both cases
+        # stdout must carry exactly ONE JSON line, and NCCL prints its version banner / INFO lines to
+        # STDOUT at communicator creation -- so fd 1 is parked on stderr while the communicator is
+        # built (the lines are not lost: they land on stderr).
+        if "NCCL_DEBUG" not in os.environ:
             os.environ["NCCL_DEBUG"] = os.environ.get("LB_NCCL_DEBUG", "WARN")
         sys.stdout.flush()
-        saved = None
-        if not external_nccl_debug:
-            saved = os.dup(1)
-            os.dup2(2, 1)
+        saved = os.dup(1)
+        os.dup2(2, 1)
         try:
             dist.init_process_group("nccl", device_id=dev)
             warm = torch.ones(1, device=dev)
@@ -343,9 +346,8 @@ def run_native(args):
             torch.cuda.synchronize()
         finally:
             sys.stdout.flush()
-            if saved is not None:
-                os.dup2(saved, 1)
-                os.close(saved)
+            os.dup2(saved, 1)
+            os.close(saved)
 
     dt = torch.bfloat16
     res = args.res

@@ -135,53 +135,82 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
   else return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4);
 }
 
-// One thread's share of a [128 x KT] weight tile: row = tid/2, columns [half*KT/2, +KT/2) of both
-// weights = 4 x 16 bytes each, fetched one tile ahead of the MMAs that consume it.
-template <typename WT>
-struct TileRegs {
-  uint4 t[4], b[4];
-};
-template <typename WT>
-__device__ __forceinline__ void load_tile(TileRegs<WT>& r, const MatDesc& m, int n, int k_first) {
-  constexpr int VEC = WTraits<WT>::VEC;
-  const bool row_ok = n < m.N;
-  const WT* wt = reinterpret_cast<const WT*>(m.wt) + static_cast<size_t>(n) * m.K;
-  const WT* wb = m.wb ? reinterpret_cast<const WT*>(m.wb) + static_cast<size_t>(n) * m.K : nullptr;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int k = k_first + i * VEC;
-    const bool ok = row_ok && k + VEC <= m.K;
-    r.t[i] = ok ? ldg16(wt + k) : make_uint4(0u, 0u, 0u, 0u);
-    r.b[i] = (ok && wb) ? ldg16(wb + k) : make_uint4(0u, 0u, 0u, 0u);
-  }
+// Weight tiles [128 rows x 128 bytes] of both models travel global -> shared through a 2-slot
+// cp.async ring (slot = 2 weights x 16 KB, raw element type), issued one whole step ahead -- at the
+// START of the step that converts the previous tile, which a register prefetch could not do without
+// doubling its registers; with 2 CTAs per SM that keeps 64 KB per SM in flight. Thread mapping:
+// 16-byte chunk c = tid & 7 of rows (tid >> 3) + 32 j, j = 0..3: a warp touches 4 full 128-byte rows
+// per instruction (coalesced in global memory, conflict-free in shared memory), and every thread later
+// reads back exactly the chunks it requested (no barrier needed for the raw data).
+constexpr int RAW_W_BYTES = TM * 128;            // one weight's tile
+constexpr int RAW_STAGE_BYTES = 2 * RAW_W_BYTES;
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void st_zero16(uint32_t dst) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(dst), "r"(0u) : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t src) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src));
+  return v;
+}
+// request the [128 x KT] tile whose first row is `row0` (rows >= row_end or >= N: zeros) and first
+// column `k0` into ring slot `slot`; one commit group per call
 template <typename WT>
-__device__ __forceinline__ void store_tile(const TileRegs<WT>& r, uint32_t s_hi, uint32_t s_lo, int row, int half) {
-  constexpr int KT = WTraits<WT>::KT;
-  if constexpr (sizeof(WT) == 2) {
+__device__ __forceinline__ void issue_tile(uint32_t raw, int slot, const MatDesc& m, int row0, int row_end, int k0) {
+  constexpr int VEC = WTraits<WT>::VEC;
+  const int c = threadIdx.x & 7;
+  const int k = k0 + c * VEC;
+  const bool k_ok = k + VEC <= m.K;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float d[8];
-      WTraits<WT>::diff(r.t[i], r.b[i], d);
-      uint32_t h[4], l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) split2(d[2 * j], d[2 * j + 1], h[j], l[j]);
-      const uint32_t off = tile_off<KT>(row, half * 4 + i);
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+  for (int j = 0; j < 4; ++j) {
+    const int r = (threadIdx.x >> 3) + 32 * j;
+    const int n = row0 + r;
+    const bool ok = k_ok && n < row_end && n < m.N;
+    const uint32_t dst = raw + slot * RAW_STAGE_BYTES + r * 128 + c * 16;
+    if (ok) {
+      cp_async16(dst, reinterpret_cast<const WT*>(m.wt) + static_cast<size_t>(n) * m.K + k);
+      if (m.wb) cp_async16(dst + RAW_W_BYTES, reinterpret_cast<const WT*>(m.wb) + static_cast<size_t>(n) * m.K + k);
+      else st_zero16(dst + RAW_W_BYTES);
+    } else {
+      st_zero16(dst);
+      st_zero16(dst + RAW_W_BYTES);
     }
-  } else {
+  }
+  cp_async_commit();
+}
+// raw slot -> (W_tuned - W_base) split into bf16 hi / lo tiles in the swizzled MMA layout
+template <typename WT>
+__device__ __forceinline__ void convert_tile(uint32_t raw, int slot, uint32_t s_hi, uint32_t s_lo) {
+  constexpr int KT = WTraits<WT>::KT;
+  const int c = threadIdx.x & 7;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      float d0[4], d1[4];
-      WTraits<WT>::diff(r.t[2 * i], r.b[2 * i], d0);
-      WTraits<WT>::diff(r.t[2 * i + 1], r.b[2 * i + 1], d1);
+  for (int j = 0; j < 4; ++j) {
+    const int r = (threadIdx.x >> 3) + 32 * j;
+    const uint32_t src = raw + slot * RAW_STAGE_BYTES + r * 128 + c * 16;
+    const uint4 t = lds16(src), b = lds16(src + RAW_W_BYTES);
+    if constexpr (sizeof(WT) == 2) {
+      float d[8];
+      WTraits<WT>::diff(t, b, d);
       uint32_t h[4], l[4];
-      split2(d0[0], d0[1], h[0], l[0]); split2(d0[2], d0[3], h[1], l[1]);
-      split2(d1[0], d1[1], h[2], l[2]); split2(d1[2], d1[3], h[3], l[3]);
-      const uint32_t off = tile_off<KT>(row, half * 2 + i);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) split2(d[2 * q], d[2 * q + 1], h[q], l[q]);
+      const uint32_t off = tile_off<KT>(r, c);
       asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
       asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+    } else {
+      float d[4];
+      WTraits<WT>::diff(t, b, d);
+      uint32_t h[2], l[2];
+      split2(d[0], d[1], h[0], l[0]);
+      split2(d[2], d[3], h[1], l[1]);
+      const uint32_t off = tile_off<KT>(r, c >> 1) + (c & 1) * 8;    // 4 fp32 = half a 16-byte bf16 chunk
+      asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(s_hi + off), "r"(h[0]), "r"(h[1]) : "memory");
+      asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(s_lo + off), "r"(l[0]), "r"(l[1]) : "memory");
     }
   }
 }
@@ -207,14 +236,14 @@ mul_right_kernel(const MatDesc* __restrict__ mats, const RItem* __restrict__ ite
   constexpr int KT = WTraits<WT>::KT;
   constexpr int TILE_BYTES = TM * KT * 2;
   constexpr int ZS_BYTES = KT * 64;
-  __shared__ __align__(128) uint8_t smem[2 * TILE_BYTES + 2 * ZS_BYTES];
-  const uint32_t s_hi = smem_u32(smem), s_lo = s_hi + TILE_BYTES;
+  extern __shared__ __align__(128) uint8_t smem[];   // [raw ring 2 x 32 KB | hi | lo | Zs hi | Zs lo]
+  const uint32_t raw = smem_u32(smem);
+  const uint32_t s_hi = raw + 2 * RAW_STAGE_BYTES, s_lo = s_hi + TILE_BYTES;
   const uint32_t z_hi = s_lo + TILE_BYTES, z_lo = z_hi + ZS_BYTES;
 
   const RItem it = items[blockIdx.x];
   const MatDesc m = mats[it.b];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = tid >> 1, half = tid & 1;
   const int nsteps = (m.K + KT - 1) / KT;
   const float* z = Zin + static_cast<size_t>(m.zoff) * L;
 
@@ -232,21 +261,23 @@ mul_right_kernel(const MatDesc* __restrict__ mats, const RItem* __restrict__ ite
   };
   (void)ZROUNDS;
 
-  TileRegs<WT> regs;
   float4 zv[2];
-  load_tile<WT>(regs, m, it.row0 + row, half * (KT / 2));
+  issue_tile<WT>(raw, 0, m, it.row0, m.N, 0);
   load_z(0, zv);
 
   float acc[4][4] = {};
   for (int step = 0; step < nsteps; ++step) {
-    __syncthreads();                                   // previous step's MMAs have read smem
-    store_tile<WT>(regs, s_hi, s_lo, row, half);
+    if (step + 1 < nsteps) {                           // next tile: requested a whole step ahead
+      issue_tile<WT>(raw, (step + 1) & 1, m, it.row0, m.N, (step + 1) * KT);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();                                   // previous step's MMAs have read the operand tiles
+    convert_tile<WT>(raw, step & 1, s_hi, s_lo);
     if (zr < KT) store_tall8(zv[0], zv[1], z_hi, z_lo, zr, zc);
     __syncthreads();
-    if (step + 1 < nsteps) {
-      load_tile<WT>(regs, m, it.row0 + row, (step + 1) * KT + half * (KT / 2));
-      load_z((step + 1) * KT, zv);
-    }
+    if (step + 1 < nsteps) load_z((step + 1) * KT, zv);
 #pragma unroll
     for (int ks = 0; ks < KT / 16; ++ks) {
       uint32_t ah[4], al[4];
@@ -315,8 +346,9 @@ mul_left_kernel(const MatDesc* __restrict__ mats, const LItem* __restrict__ item
   constexpr int NT = KT / 32;                           // n8 tiles per warp: 2 (KT 64) or 1 (KT 32)
   constexpr int TILE_BYTES = TM * KT * 2;
   constexpr int QS_BYTES = TM * 64;
-  __shared__ __align__(128) uint8_t smem[2 * TILE_BYTES + 2 * QS_BYTES];
-  const uint32_t s_hi = smem_u32(smem), s_lo = s_hi + TILE_BYTES;
+  extern __shared__ __align__(128) uint8_t smem[];   // [raw ring 2 x 32 KB | hi | lo | Qs hi | Qs lo]
+  const uint32_t raw = smem_u32(smem);
+  const uint32_t s_hi = raw + 2 * RAW_STAGE_BYTES, s_lo = s_hi + TILE_BYTES;
   const uint32_t q_hi = s_lo + TILE_BYTES, q_lo = q_hi + QS_BYTES;
 
   const LItem it = items[blockIdx.x];
@@ -337,24 +369,25 @@ mul_left_kernel(const MatDesc* __restrict__ mats, const LItem* __restrict__ item
       v[0] = v[1] = v[2] = v[3] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
-  // rows beyond the slab are masked through Q (zero rows); the weight rows themselves are only
-  // guarded against the matrix end
-  TileRegs<WT> regs;
+  // rows beyond the slab are zero in both operands (Q rows and weight tile rows)
   float4 qv[4];
-  load_tile<WT>(regs, m, it.n0 + row, it.k0 + half * (KT / 2));
+  issue_tile<WT>(raw, 0, m, it.n0, it.n1, it.k0);
   load_q(it.n0, qv);
 
   float acc[NT][4] = {};
   for (int step = 0; step < nsteps; ++step) {
+    if (step + 1 < nsteps) {
+      issue_tile<WT>(raw, (step + 1) & 1, m, it.n0 + (step + 1) * TM, it.n1, it.k0);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
-    store_tile<WT>(regs, s_hi, s_lo, row, half);
+    convert_tile<WT>(raw, step & 1, s_hi, s_lo);
     store_tall8(qv[0], qv[1], q_hi, q_lo, row, half * 2);
     store_tall8(qv[2], qv[3], q_hi, q_lo, row, half * 2 + 1);
     __syncthreads();
-    if (step + 1 < nsteps) {
-      load_tile<WT>(regs, m, it.n0 + (step + 1) * TM + row, it.k0 + half * (KT / 2));
-      load_q(it.n0 + (step + 1) * TM, qv);
-    }
+    if (step + 1 < nsteps) load_q(it.n0 + (step + 1) * TM, qv);
 #pragma unroll
     for (int ks = 0; ks < TM / 16; ++ks) {
       // A = Q^T: a0 (m 0-7, kk 0-7), a1 (m 8-15, kk 0-7), a2 (m 0-7, kk 8-15), a3 (m 8-15, kk 8-15);
@@ -501,7 +534,8 @@ tall_transform_kernel(const MatDesc* __restrict__ mats, const TItem* __restrict_
 // disjoint rotations of a step are applied in parallel: thread = (rotation k = tid/16, index
 // tid%16 and +16). Outputs eigenvectors (columns, descending eigenvalue) and sqrt(max(eig, 0)).
 __global__ void __launch_bounds__(256)
-jacobi32_kernel(const float* __restrict__ G, float* __restrict__ V, float* __restrict__ sigma, int sweeps) {
+jacobi32_kernel(const float* __restrict__ G, float* __restrict__ V, float* __restrict__ sigma, int sweeps,
+                float tol) {
   __shared__ float A[L][L + 1];
   __shared__ float Q[L][L + 1];
   __shared__ int perm[L];
@@ -516,6 +550,9 @@ jacobi32_kernel(const float* __restrict__ G, float* __restrict__ V, float* __res
   if (tid < L) perm[tid] = tid;
   __syncthreads();
   const int k = tid >> 4, idx = tid & 15;
+  __shared__ float off_max[2];     // largest relative off-diagonal seen in the current sweep (by parity)
+  if (tid < 2) off_max[tid] = 0.f;
+  __syncthreads();
   for (int sw = 0; sw < sweeps; ++sw) {
     for (int step = 0; step < L - 1; ++step) {
       if (tid < 16) {
@@ -530,6 +567,10 @@ jacobi32_kernel(const float* __restrict__ G, float* __restrict__ V, float* __res
           s = tt * c;
         }
         cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
+        float rel = fabsf(apq) * rsqrtf(fmaxf(fabsf(app * aqq), 1e-37f));
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) rel = fmaxf(rel, __shfl_xor_sync(0x0000ffffu, rel, o));
+        if (tid == 0) off_max[sw & 1] = fmaxf(off_max[sw & 1], rel);
       }
       __syncthreads();
       {
@@ -564,6 +605,11 @@ jacobi32_kernel(const float* __restrict__ G, float* __restrict__ V, float* __res
       if (tid < L) perm[tid] = nxt;
       __syncthreads();
     }
+    // converged: every off-diagonal met in this sweep was below fp32 resolution of its diagonal pair
+    const float seen = off_max[sw & 1];
+    if (tid == 0) off_max[(sw + 1) & 1] = 0.f;
+    __syncthreads();
+    if (seen < tol) break;
   }
   if (tid < L) {
     const float w = A[tid][tid];
@@ -808,24 +854,47 @@ extern "C" int lb_svd_truncated_batched(const void* const* Wt, const void* const
   const int nR = static_cast<int>(p.ritems.size()), nL = static_cast<int>(p.litems.size());
   const int nTy = static_cast<int>(p.ty.size()), nTz = static_cast<int>(p.tz.size());
 
+  // dynamic shared memory: raw ring 64 KB + converted hi/lo tiles + the tall-skinny chunk (hi/lo)
+  const int tile_bytes = TM * kt * 2;
+  const int smem_r = 2 * RAW_STAGE_BYTES + 2 * tile_bytes + 2 * kt * 64;
+  const int smem_l = 2 * RAW_STAGE_BYTES + 2 * tile_bytes + 2 * TM * 64;
+  static unsigned long long attr_done = 0;      // bit per device ordinal
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return LB_ERR_CUDA;
+    if (dev < 0 || dev >= 64 || !((attr_done >> dev) & 1ull)) {
+      const int big_r = 2 * RAW_STAGE_BYTES + 2 * TM * 64 * 2 + 2 * 64 * 64;
+      const int big_l = 2 * RAW_STAGE_BYTES + 2 * TM * 64 * 2 + 2 * TM * 64;
+      if (cudaFuncSetAttribute(mul_right_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_r) != cudaSuccess ||
+          cudaFuncSetAttribute(mul_right_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_r) != cudaSuccess ||
+          cudaFuncSetAttribute(mul_right_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_r) != cudaSuccess ||
+          cudaFuncSetAttribute(mul_left_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_l) != cudaSuccess ||
+          cudaFuncSetAttribute(mul_left_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_l) != cudaSuccess ||
+          cudaFuncSetAttribute(mul_left_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_l) != cudaSuccess)
+        return LB_ERR_CUDA;
+      if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
+    }
+  }
   auto mul_right = [&](bool gram) -> bool {
     if (gram && cudaMemsetAsync(G, 0, g_bytes, st) != cudaSuccess) return false;
     float* g = gram ? G : nullptr;
-    if (w_dtype == LB_F16) mul_right_kernel<__half><<<nR, THREADS, 0, st>>>(mats, ritems, Z, Y, g);
-    else if (w_dtype == LB_BF16) mul_right_kernel<__nv_bfloat16><<<nR, THREADS, 0, st>>>(mats, ritems, Z, Y, g);
-    else mul_right_kernel<float><<<nR, THREADS, 0, st>>>(mats, ritems, Z, Y, g);
+    if (w_dtype == LB_F16) mul_right_kernel<__half><<<nR, THREADS, smem_r, st>>>(mats, ritems, Z, Y, g);
+    else if (w_dtype == LB_BF16) mul_right_kernel<__nv_bfloat16><<<nR, THREADS, smem_r, st>>>(mats, ritems, Z, Y, g);
+    else mul_right_kernel<float><<<nR, THREADS, smem_r, st>>>(mats, ritems, Z, Y, g);
     return cudaGetLastError() == cudaSuccess;
   };
   auto mul_left = [&]() -> bool {
     if (cudaMemsetAsync(Z, 0, static_cast<size_t>(p.sumK) * L * 4, st) != cudaSuccess) return false;
-    if (w_dtype == LB_F16) mul_left_kernel<__half><<<nL, THREADS, 0, st>>>(mats, litems, Y, Z);
-    else if (w_dtype == LB_BF16) mul_left_kernel<__nv_bfloat16><<<nL, THREADS, 0, st>>>(mats, litems, Y, Z);
-    else mul_left_kernel<float><<<nL, THREADS, 0, st>>>(mats, litems, Y, Z);
+    if (w_dtype == LB_F16) mul_left_kernel<__half><<<nL, THREADS, smem_l, st>>>(mats, litems, Y, Z);
+    else if (w_dtype == LB_BF16) mul_left_kernel<__nv_bfloat16><<<nL, THREADS, smem_l, st>>>(mats, litems, Y, Z);
+    else mul_left_kernel<float><<<nL, THREADS, smem_l, st>>>(mats, litems, Y, Z);
     return cudaGetLastError() == cudaSuccess;
   };
   // orth(buf): [Gram given in G] -> Jacobi -> buf <- buf V diag(1/s) (+ Gram of the result)
-  auto jacobi = [&](int sweeps) -> bool {
-    jacobi32_kernel<<<batch, 256, 0, st>>>(G, V, sig, sweeps);
+  // at most `sweeps` cyclic sweeps; stops after the first sweep whose rotations were all below `tol`
+  // (relative off-diagonal): 1e-4 is plenty for an intermediate basis, 1e-7 (fp32) for the last two
+  auto jacobi = [&](int sweeps, float tol) -> bool {
+    jacobi32_kernel<<<batch, 256, 0, st>>>(G, V, sig, sweeps, tol);
     return cudaGetLastError() == cudaSuccess;
   };
   auto transform = [&](int space, bool mul, bool gram) -> bool {
@@ -839,15 +908,15 @@ extern "C" int lb_svd_truncated_batched(const void* const* Wt, const void* const
   LB_SVD_CHECK();
   if (!mul_right(true)) return LB_ERR_CUDA;                       // Y = dW Om, G = Y^T Y
   for (int it = 0; it < power_iters; ++it) {
-    if (!jacobi(6) || !transform(0, true, false)) return LB_ERR_CUDA;    // Y <- orth(Y)
+    if (!jacobi(6, 1e-4f) || !transform(0, true, false)) return LB_ERR_CUDA;    // Y <- orth(Y)
     if (!mul_left()) return LB_ERR_CUDA;                                   // Z = dW^T Y
-    if (!transform(1, false, true) || !jacobi(6) || !transform(1, true, false)) return LB_ERR_CUDA;   // Z <- orth(Z)
+    if (!transform(1, false, true) || !jacobi(6, 1e-4f) || !transform(1, true, false)) return LB_ERR_CUDA;   // Z <- orth(Z)
     if (!mul_right(true)) return LB_ERR_CUDA;                              // Y = dW Z, G
   }
   // Q = orth2(Y): the basis the projected problem is solved in must be orthonormal to fp32 accuracy
-  if (!jacobi(6) || !transform(0, true, true) || !jacobi(6) || !transform(0, true, false)) return LB_ERR_CUDA;
+  if (!jacobi(6, 1e-4f) || !transform(0, true, true) || !jacobi(8, 1e-7f) || !transform(0, true, false)) return LB_ERR_CUDA;
   if (!mul_left()) return LB_ERR_CUDA;                                     // B^T = dW^T Q
-  if (!transform(1, false, true) || !jacobi(10)) return LB_ERR_CUDA;       // B B^T = Uh diag(s^2) Uh^T
+  if (!transform(1, false, true) || !jacobi(10, 1e-7f)) return LB_ERR_CUDA;       // B B^T = Uh diag(s^2) Uh^T
   factors_kernel<<<nTy, THREADS, 0, st>>>(mats, ty, 0, Y, V, sig, rank, out);
   LB_SVD_CHECK();
   factors_kernel<<<nTz, THREADS, 0, st>>>(mats, tz, 1, Z, V, sig, rank, out);
