@@ -182,6 +182,16 @@ class _GroupedLoraLinearFn(torch.autograd.Function):
         return (dx, None, *grads)
 
 
+def _site_sig(m):
+    """Everything of a site that the parked output depends on besides the input: if any of it is
+    edited between the family's launch and the sibling's own call (an external `.weight = ...`,
+    an in-place update, tune_lora_scale, set_lora_diag), the parked result is stale."""
+    from .modules import _key as mkey
+    sel = m.selector
+    return (mkey(m.linear.weight), mkey(m.linear.bias), mkey(m.lora_down.weight), mkey(m.lora_up.weight),
+            float(m.scale), mkey(getattr(sel, "weight", None)), m.training, m.dropout.p)
+
+
 def forward_maybe_grouped(site, x):
     """Returns the site's output if it was served by / started a grouped launch, else None."""
     ref = site._lb.parent
@@ -194,7 +204,7 @@ def forward_maybe_grouped(site, x):
         par.__dict__["_lb_groups"] = st
     k = _key(x)
     ent = st.cache.pop(id(site), None)
-    if ent is not None and ent[0] == k:
+    if ent is not None and ent[0] == k and ent[3] == _site_sig(site):
         return ent[2]
     if not st.learned:
         if any(s is site for s, _ in st.trace):
@@ -222,5 +232,5 @@ def forward_maybe_grouped(site, x):
         if m is site:
             ret = y
         else:
-            st.cache[id(m)] = (k, x, y)
+            st.cache[id(m)] = (k, x, y, _site_sig(m))
     return ret

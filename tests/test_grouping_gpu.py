@@ -105,6 +105,44 @@ def test_sibling_with_a_different_input_computes_alone():
     assert rel(k2, O.lora_linear_forward(x, att.to_k.linear.weight, None, att.to_k.lora_down.weight, att.to_k.lora_up.weight, 1.0)) < 2 ** -7
 
 
+def test_sibling_edited_between_the_two_calls_is_not_served_stale():
+    """The family is launched at the FIRST sibling's call; a sibling whose scale / factors / frozen
+    weight are edited before its own call must not receive the parked (now stale) output."""
+    import lora_b200 as L
+    from oracle import lora_ops as O
+
+    class Attention(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.to_q = nn.Linear(320, 320, bias=False)
+            self.to_k = nn.Linear(320, 320, bias=False)
+
+    torch.manual_seed(0)
+    att = Attention().to(DEV).to(torch.bfloat16)
+    L.inject_trainable_lora(att, r=4)
+    for m in (att.to_q, att.to_k):
+        m.lora_up.weight.data.normal_(0, 0.05)
+    L.set_grouping(True)
+    x = torch.randn(256, 320, device=DEV, dtype=torch.bfloat16)
+    for _ in range(2):
+        att.to_q(x); att.to_k(x)
+
+    def want(m, scale):
+        return O.lora_linear_forward(x, m.linear.weight, None, m.lora_down.weight, m.lora_up.weight, scale)
+
+    att.to_q(x)                                   # launches the family, parks k's output
+    att.to_k.scale = 0.25                         # tune_lora_scale on one sibling
+    assert rel(att.to_k(x), want(att.to_k, 0.25)) < 2 ** -7
+    att.to_q(x)
+    with torch.no_grad():
+        att.to_k.lora_up.weight.mul_(3.0)         # in-place factor edit (version bump)
+    assert rel(att.to_k(x), want(att.to_k, 0.25)) < 2 ** -7
+    att.to_q(x)
+    att.to_k.linear.weight = nn.Parameter(torch.randn(320, 320, device=DEV, dtype=torch.bfloat16) * 0.05,
+                                          requires_grad=False)     # external re-assignment (lora.py:290)
+    assert rel(att.to_k(x), want(att.to_k, 0.25)) < 2 ** -7
+
+
 def test_training_step_with_grouping_matches_without():
     import lora_b200 as L
     from lora_b200.host.clip import build_text_encoder
