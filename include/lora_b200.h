@@ -130,6 +130,11 @@ typedef struct lb_wgrad_problem {
   const float* diag;    /* selector diagonal [r] or NULL                   */
   float drop_p;
   const void* seed_dev; /* device uint64 (drop_p > 0) or NULL              */
+  /* conv_H > 0: the lora_down weight-gradient of a conv site (lb_lora_wgrad_conv as one problem):
+   * S = NHWC input rows [M/(H*W), H, W, C], every tap (ty, tx) of the kh x kw filter reads the pixel
+   * shifted by (ty - pad_h, tx - pad_w), out = dA[r, C, kh, kw] flat with out_js = C*kh*kw,
+   * out_cs = kh*kw (+ tap). 0: plain rows. */
+  int conv_H, conv_W, kh, kw, pad_h, pad_w;
 } lb_wgrad_problem;
 
 /* n independent reductions (HOST array) in ceil(n/24) launches. The step engine queues the dA / dB

@@ -124,7 +124,7 @@ class _FusedLoraConv2dFn(torch.autograd.Function):
         if need_a:
             tgt = sink[0] if sink is not None else torch.zeros((r, cin * taps), device=gy.device,
                                                                dtype=torch.float32)
-            ops.wgrad_conv(x16, dTs, ctx.diag, ctx.scale, tgt, r, cin, h, w, kh, kw, ph, pw)
+            ops.wgrad_conv(x16, dTs, ctx.diag, ctx.scale, tgt, r, cin, h, w, kh, kw, ph, pw, async_ok=sink is not None)
             if sink is None:
                 dA = tgt.view_as(A).to(A.dtype)
         if need_b:

@@ -224,7 +224,9 @@ static int linear_fwd_impl(const void* X, const void* W, const float* bias,
   }
   const int sched = g_linear_mode & 3, bn_choice = (g_linear_mode >> 2) & 3, split_choice = g_linear_mode >> 4;
   const long long tiles128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
-  bool narrow = tiles128 < 120;  // not enough 128-wide tiles to fill 148 SMs: halve BLOCK_N
+  // not enough 128-wide tiles to fill the SMs: halve BLOCK_N. 90-148 tiles of 128 (4096x320->320:
+  // 96) run better as ONE wave of 128-wide tiles than as 160 64-wide tiles at 3 CTAs/SM (r1c: 11.1 vs 12.3 us)
+  bool narrow = tiles128 < 90;
   if (K >= 2048 && tiles128 >= 64) narrow = false;  // long K: per-tile work is large, keep W reuse
   if (bn_choice == 1) narrow = true;
   if (bn_choice == 2) narrow = false;

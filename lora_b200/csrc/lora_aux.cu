@@ -59,6 +59,10 @@ struct WgProblem {
   int r;
   int M;               // rows of this problem (0: the launch-wide WgArgs::M)
   const unsigned long long* seed;  // mask seed of this problem (null: the launch-wide seed_dev)
+  // conv weight-gradient: rows of S are pixels of NHWC images [M/(cH*cW), cH, cW, C] read at the
+  // pixel shifted by (dy, dx) (zero outside the image); taps > 1: blockIdx.z = filter tap t with
+  // shift (dy + t/kw, dx + t%kw) and out += t. cH == 0: plain rows.
+  int cH, cW, dy, dx, kw, taps;
 };
 constexpr int WG_MAXP = 24;
 struct WgArgs {
@@ -67,8 +71,6 @@ struct WgArgs {
   int n_pr;
   const unsigned long long* seed_dev;
   int M, fmt;
-  int cH, cW, dy, dx;  // conv tap shift of problem 0 (cH == 0: none)
-  int kw, taps;        // taps > 1: blockIdx.z = filter tap t: shift (dy + t/kw, dx + t%kw), out += t
   int slabs;           // 64-row slabs per CTA
 };
 
@@ -88,9 +90,11 @@ wgrad_kernel(const WgArgs a) {
   const bool col_ok = c0 < C;                          // C % 8 == 0 => whole 4-column group valid
   const bool f32in = a.fmt == 2;                       // fp32 rows: 16 bytes per lane
   const size_t pitch = static_cast<size_t>(C) >> 2;    // row pitch in 8-byte words (16-bit rows)
-  const int cH = which ? 0 : a.cH;
-  const int tap = (cH > 0 && a.taps > 1) ? blockIdx.z : 0;
-  const int sdy = a.dy + (a.taps > 1 ? tap / a.kw : 0), sdx = a.dx + (a.taps > 1 ? tap % a.kw : 0);
+  const int cH = P.cH, cW = P.cW;
+  const int ntaps = (cH > 0 && P.taps > 1) ? P.taps : 1;
+  if (static_cast<int>(blockIdx.z) >= ntaps) return;     // grid.z = most taps of any problem in the launch
+  const int tap = blockIdx.z;
+  const int sdy = P.dy + (ntaps > 1 ? tap / P.kw : 0), sdx = P.dx + (ntaps > 1 ? tap % P.kw : 0);
   for (int i = threadIdx.x; i < RQ * 4 * WG_COLS; i += WG_WARPS * 32) (&red[0][0])[i] = 0.f;
   __syncthreads();
 
@@ -112,9 +116,9 @@ wgrad_kernel(const WgArgs a) {
       if (cH > 0 && ok) {
         // conv weight-gradient tap: row m is pixel (h, w) of an NHWC image; S is read at the pixel
         // shifted by (dy, dx), zero outside the image (= the convolution's zero padding)
-        const int ww = m % a.cW + sdx, hh = (m / a.cW) % cH + sdy;
-        ok = hh >= 0 && hh < cH && ww >= 0 && ww < a.cW;
-        src = static_cast<long long>(m) + sdy * a.cW + sdx;
+        const int ww = m % cW + sdx, hh = (m / cW) % cH + sdy;
+        ok = hh >= 0 && hh < cH && ww >= 0 && ww < cW;
+        src = static_cast<long long>(m) + sdy * cW + sdx;
       }
       if (!ok) {
         raw[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -896,7 +900,10 @@ static int wgrad_run(WgArgs& a, int in_dtype, void* stream) {
   int slabs = 1;
   while (slabs < 8 && static_cast<long long>(nblk) * ((slabs_total + 2 * slabs - 1) / (2 * slabs)) >= 296) slabs *= 2;
   a.slabs = slabs;
-  dim3 grid(nblk, (slabs_total + slabs - 1) / slabs, a.taps > 1 ? a.taps : 1);
+  int max_taps = 1;
+  for (int i = 0; i < a.n_pr; ++i)
+    if (a.pr[i].cH > 0 && a.pr[i].taps > max_taps) max_taps = a.pr[i].taps;
+  dim3 grid(nblk, (slabs_total + slabs - 1) / slabs, max_taps);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch ((rmax + 3) / 4) {
     case 1: wgrad_kernel<1><<<grid, WG_WARPS * 32, 0, st>>>(a); break;
@@ -919,7 +926,7 @@ static int wgrad_launch(const void* S, const float* V, const float* diag, float 
   a.pr[0].diag = diag; a.pr[0].scale = scale; a.pr[0].r = r;
   a.n_pr = 1;
   a.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
-  a.M = M; a.cH = H; a.cW = W; a.dy = dy; a.dx = dx;
+  a.M = M; a.pr[0].cH = H; a.pr[0].cW = W; a.pr[0].dy = dy; a.pr[0].dx = dx; a.pr[0].kw = 1; a.pr[0].taps = 1;
   return wgrad_run(a, in_dtype, stream);
 }
 
@@ -935,7 +942,7 @@ extern "C" int lb_lora_wgrad_conv(const void* S, const float* V, const float* di
   a.pr[0].js = static_cast<long long>(C) * taps; a.pr[0].cs = taps; a.pr[0].C = C; a.pr[0].drop_p = 0.f;
   a.pr[0].diag = diag; a.pr[0].scale = scale; a.pr[0].r = r;
   a.n_pr = 1;
-  a.M = M; a.cH = H; a.cW = W; a.dy = -pad_h; a.dx = -pad_w; a.kw = kw; a.taps = taps;
+  a.M = M; a.pr[0].cH = H; a.pr[0].cW = W; a.pr[0].dy = -pad_h; a.pr[0].dx = -pad_w; a.pr[0].kw = kw; a.pr[0].taps = taps;
   return wgrad_run(a, in_dtype, stream);
 }
 
@@ -997,6 +1004,10 @@ extern "C" int lb_lora_wgrad_batch(const lb_wgrad_problem* probs, int n, int in_
       w.S = reinterpret_cast<const uint2*>(q.S); w.V = q.V; w.out = q.out; w.js = q.out_js; w.cs = q.out_cs;
       w.C = q.C; w.drop_p = q.drop_p; w.diag = q.diag; w.scale = q.scale; w.r = q.r; w.M = q.M;
       w.seed = reinterpret_cast<const unsigned long long*>(q.seed_dev);
+      if (q.conv_H > 0) {       // conv lora_down weight-gradient: all taps of one site as one problem
+        if (q.conv_W <= 0 || q.kh <= 0 || q.kw <= 0 || (q.M % (q.conv_H * q.conv_W)) != 0) return LB_ERR_SHAPE;
+        w.cH = q.conv_H; w.cW = q.conv_W; w.dy = -q.pad_h; w.dx = -q.pad_w; w.kw = q.kw; w.taps = q.kh * q.kw;
+      }
       max_m = q.M > max_m ? q.M : max_m;
     }
     a.n_pr = cnt;

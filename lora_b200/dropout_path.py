@@ -178,7 +178,7 @@ class _LoraConv2dDropoutFn(torch.autograd.Function):
         dA = dB = None
         if need_a:
             tgt = sink[0] if sink is not None else torch.zeros((r, cin * taps), device=gy.device, dtype=torch.float32)
-            ops.wgrad_conv(x16, dTs, ctx.diag, ctx.scale, tgt, r, cin, h, w, kh, kw, ph, pw)
+            ops.wgrad_conv(x16, dTs, ctx.diag, ctx.scale, tgt, r, cin, h, w, kh, kw, ph, pw, async_ok=sink is not None)
             if sink is None:
                 dA = tgt.view_as(A).to(A.dtype)
         if need_b:

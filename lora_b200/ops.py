@@ -42,7 +42,9 @@ class _WgProblemC(_ct.Structure):
     _fields_ = [("S", _ct.c_void_p), ("V", _ct.c_void_p), ("out", _ct.c_void_p),
                 ("out_js", _ct.c_longlong), ("out_cs", _ct.c_longlong),
                 ("M", _ct.c_int), ("C", _ct.c_int), ("r", _ct.c_int), ("scale", _ct.c_float),
-                ("diag", _ct.c_void_p), ("drop_p", _ct.c_float), ("seed_dev", _ct.c_void_p)]
+                ("diag", _ct.c_void_p), ("drop_p", _ct.c_float), ("seed_dev", _ct.c_void_p),
+                ("conv_H", _ct.c_int), ("conv_W", _ct.c_int), ("kh", _ct.c_int), ("kw", _ct.c_int),
+                ("pad_h", _ct.c_int), ("pad_w", _ct.c_int)]
 
 
 _WG_QUEUE = None      # None: launch immediately; dict dtype -> [(_WgProblemC fields, keepalive)]
@@ -58,10 +60,10 @@ def wgrad_defer_cancel():
     _WG_QUEUE = None
 
 
-def _wgrad_enqueue(S, V, out, out_js, out_cs, M, C, r, scale, diag, drop_p=0.0, seed=None):
+def _wgrad_enqueue(S, V, out, out_js, out_cs, M, C, r, scale, diag, drop_p=0.0, seed=None, conv=None):
     dp = lambda t: None if t is None else t.data_ptr()
     item = (dp(S), dp(V), dp(out), int(out_js), int(out_cs), int(M), int(C), int(r), float(scale), dp(diag),
-            float(drop_p), dp(seed))
+            float(drop_p), dp(seed)) + (tuple(int(v) for v in conv) if conv is not None else (0, 0, 0, 0, 0, 0))
     _WG_QUEUE.setdefault(S.dtype, []).append((item, (S, V, out, diag, seed)))
 
 
@@ -401,10 +403,14 @@ def wgrad_multi(x2d: torch.Tensor, items, async_ok: bool = False):
 
 
 def wgrad_conv(x_nhwc_rows: torch.Tensor, V: torch.Tensor, diag, scale: float, out: torch.Tensor, r: int,
-               C: int, H: int, W: int, kh: int, kw: int, pad_h: int, pad_w: int):
+               C: int, H: int, W: int, kh: int, kw: int, pad_h: int, pad_w: int, async_ok: bool = False):
     """dA [r, C*kh*kw] (flat [r,Cin,kh,kw]) += all taps, one launch (see lb_lora_wgrad_conv)."""
     _req_cuda(x_nhwc_rows, V, out)
     M = V.shape[0]
+    if _WG_QUEUE is not None and async_ok:
+        _wgrad_enqueue(x_nhwc_rows, V, out, C * kh * kw, kh * kw, M, C, r, scale, diag,
+                       conv=(H, W, kh, kw, pad_h, pad_w))
+        return
     check(_C.lib.lb_lora_wgrad_conv(ptr(x_nhwc_rows), ptr(V), ptr(diag), float(scale), ptr(out), M, C, r,
                                     H, W, kh, kw, pad_h, pad_w, dtype_code(x_nhwc_rows.dtype), stream_ptr()),
           "lb_lora_wgrad_conv")
