@@ -74,11 +74,14 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 #define LB_STAMP(i) do { if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0) p.dbg[i] = gtimer(); } while (0)
 
-template <int BLOCK_N, int STAGES, typename OutT, int G, bool DROP = false>
+template <int BLOCK_N, int STAGES, typename OutT, int G, bool DROP = false, bool BMASK = false>
 struct Smem {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = (BLOCK_N + R_PAD) * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  // BMASK (dropout backward): every stage also holds the MASKED copy of the A tile (mask o gY), the
+  // operand of the T MMA; the TMA transaction still covers A + B only
+  static constexpr int TX_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES + (BMASK ? A_BYTES : 0);
   static constexpr int BOX_COLS = 128 / sizeof(OutT);  // columns per 128-byte store box
   static constexpr int NUM_BOXES = BLOCK_N / BOX_COLS;
   static constexpr int BOX_BYTES = BLOCK_M * 128;
@@ -93,7 +96,7 @@ struct Smem {
       (NUM_BOXES * BOX_BYTES > T_BYTES + UP_BYTES) ? NUM_BOXES * BOX_BYTES : T_BYTES + UP_BYTES;
   static constexpr int OFF_BIAS = OFF_EPI + ((EPI_BYTES + 1023) / 1024) * 1024;
   static constexpr int OFF_BAR = OFF_BIAS + BLOCK_N * 4;
-  static constexpr int NUM_BARS = 2 * STAGES + 3;
+  static constexpr int NUM_BARS = 2 * STAGES + 3 + (BMASK ? STAGES : 0);
   static constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
   static constexpr int TOTAL = OFF_TMEM + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
@@ -107,11 +110,13 @@ struct Smem {
 };
 
 // One output tile (n_blk, m_blk) of one problem; called by the single-problem and the grouped kernel.
-template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G, bool DROP = false, bool SPLITK = false>
+template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G, bool DROP = false, bool SPLITK = false,
+          bool BMASK = false>
 __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtensorMap& tmW,
                                            const CUtensorMap& tmD, const CUtensorMap& tmY,
                                            const FusedParams& p, const int n_blk, const int m_blk) {
-  using S = Smem<BLOCK_N, STAGES, OutT, G, DROP>;
+  using S = Smem<BLOCK_N, STAGES, OutT, G, DROP, BMASK>;
+  static_assert(!(BMASK && DROP), "BMASK is the backward of DROP");
   constexpr int PCOLS = BLOCK_N + R_PAD * G;          // columns of one partial accumulator
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -143,6 +148,7 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
   const uint32_t bar_acc = sbase + S::OFF_BAR + 8 * (2 * STAGES + 0);     // K loop finished
   const uint32_t bar_tready = sbase + S::OFF_BAR + 8 * (2 * STAGES + 1);  // T' operand(s) in smem
   const uint32_t bar_final = sbase + S::OFF_BAR + 8 * (2 * STAGES + 2);   // LoRA MMAs finished
+  auto bar_masked = [&](int s) { return sbase + S::OFF_BAR + 8 * (2 * STAGES + 3 + s); };  // BMASK: masked A tile ready
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + S::OFF_TMEM);
 
   if (warp == 0 && lane == 0) {
@@ -157,6 +163,8 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
     mbar_init(bar_acc, 1);
     mbar_init(bar_tready, EPI_THREADS);
     mbar_init(bar_final, 1);
+    if constexpr (BMASK)
+      for (int s = 0; s < STAGES; ++s) mbar_init(bar_masked(s), EPI_THREADS);
     fence_mbar_init();
   }
   __syncthreads();  // barriers initialised
@@ -185,7 +193,7 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(bar_empty(s), ph ^ 1);
-        mbar_expect_tx(bar_full(s), S::STAGE_BYTES);
+        mbar_expect_tx(bar_full(s), S::TX_BYTES);
         const uint32_t sa = sbase + s * S::STAGE_BYTES;
         const uint32_t sb = sa + S::A_BYTES;
         if constexpr (CONV) {
@@ -225,12 +233,28 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
           // K-major SWIZZLE_128B: 8-row groups 1024 B apart; one K-step = 32 B along the row
           const uint64_t ad = umma_smem_desc(sa + k * UMMA_K * 2, 16, 1024, 2);
           const uint64_t bd = umma_smem_desc(sb + k * UMMA_K * 2, 16, 1024, 2);
-          if constexpr (G == 1) {
+          if constexpr (BMASK) {
+            umma_f16_ss(tmem, ad, bd, idesc_base, (it | k) != 0);       // base only; T below, from the masked tile
+          } else if constexpr (G == 1) {
             umma_f16_ss(tmem, ad, bd, idesc_wide, (it | k) != 0);
           } else {
             const uint64_t dd = umma_smem_desc(sb + BLOCK_N * 128 + k * UMMA_K * 2, 16, 1024, 2);
             umma_f16_ss(tmem, ad, bd, idesc_base, (it | k) != 0);
             umma_f16_ss(tmem + BLOCK_N + R_PAD * tap, ad, dd, idesc_t, !(tap_first && k == 0));
+          }
+        }
+        if constexpr (BMASK) {
+          // T_tap += (mask o gY tile) . D^T : the epilogue warps have written the masked copy of this
+          // stage's A tile next to it (same swizzled layout)
+          mbar_wait(bar_masked(s), ph);
+          tc_fence_after();
+          const uint32_t sm = sb + S::B_BYTES;
+          const bool first = (G > 1) ? tap_first : (it == 0);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t amd = umma_smem_desc(sm + k * UMMA_K * 2, 16, 1024, 2);
+            const uint64_t dd = umma_smem_desc(sb + BLOCK_N * 128 + k * UMMA_K * 2, 16, 1024, 2);
+            umma_f16_ss(tmem + BLOCK_N + R_PAD * tap, amd, dd, idesc_t, !(first && k == 0));
           }
         }
         umma_commit(bar_empty(s));  // frees the smem slot when these MMAs retire
@@ -287,7 +311,7 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
     float coef[R_PAD];
 #pragma unroll
     for (int j = 0; j < R_PAD; ++j)
-      coef[j] = (j < p.r) ? p.scale * (p.diag ? __ldg(p.diag + j) : 1.f) : 0.f;
+      coef[j] = (j < p.r) ? p.scale * (p.diag ? __ldg(p.diag + j) : 1.f) * (BMASK ? p.drop_inv : 1.f) : 0.f;
 
     // global row (pixel) this thread owns, for the T side output
     long long grow = -1;
@@ -296,6 +320,63 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
       if (hh < p.H && ww < p.W) grow = (static_cast<long long>(img) * p.H + hh) * p.W + ww;
     } else {
       if (m0 + row < p.M) grow = m0 + row;
+    }
+
+    if constexpr (BMASK) {
+      // Dropout backward: dT = (mask o gY / (1-p)) . B needs the MASKED gY tile as the T MMA's A
+      // operand. These four warps are idle during the K loop, so they produce it: for every stage,
+      // copy the TMA-landed tile (128 rows x 64 columns, 128B-swizzled) into the stage's second buffer
+      // with the dropped elements zeroed (same counter hash as the forward drain; 1/(1-p) is folded
+      // into coef below), then hand it to the MMA warp. Thread -> logical 16-byte chunk (et & 7) of
+      // rows (et >> 3) + 16 i: conflict-free in shared memory.
+      const unsigned long long msd = __ldg(p.seed);
+      const uint32_t ms0 = static_cast<uint32_t>(msd), ms1 = static_cast<uint32_t>(msd >> 32);
+      const uint32_t mthr = drop_threshold(p.drop_p);
+      const int mc = et & 7;
+      const unsigned long long ncols = CONV ? p.C : p.K;      // row pitch of the mask = columns of gY
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int it = kb - kb_begin;
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(bar_full(s), ph);
+        const uint32_t sa = sbase + s * S::STAGE_BYTES;
+        const uint32_t sm = sa + S::A_BYTES + S::B_BYTES;
+        int tdy = 0, tdx = 0, col0 = kb * BLOCK_K;
+        if constexpr (CONV) {
+          const int tap = kb / cblocks, cb = kb - tap * cblocks;
+          tdy = tap / p.kw - p.pad_h;
+          tdx = tap % p.kw - p.pad_w;
+          col0 = cb * BLOCK_K;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = (et >> 3) + 16 * i;
+          long long gr = -1;
+          if constexpr (CONV) {
+            const int hh = h0 + r / p.TW + tdy, ww = w0 + r % p.TW + tdx;
+            if (hh >= 0 && hh < p.H && ww >= 0 && ww < p.W) gr = (static_cast<long long>(img) * p.H + hh) * p.W + ww;
+          } else {
+            if (m0 + r < p.M) gr = m0 + r;
+          }
+          const uint32_t off = r * 128 + ((mc ^ (r & 7)) << 4);
+          uint32_t w0_, w1_, w2_, w3_;
+          asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(w0_), "=r"(w1_), "=r"(w2_), "=r"(w3_) : "r"(sa + off));
+          if (gr >= 0) {
+            const unsigned long long e0 = (static_cast<unsigned long long>(gr) * ncols + col0 + mc * 8) >> 1;
+            uint32_t wv[4] = {w0_, w1_, w2_, w3_};
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+              const uint32_t bits = drop_bits(ms0, ms1, e0 + qd);
+              const uint32_t keep = ((bits & 0xffffu) >= mthr ? 0x0000ffffu : 0u) | ((bits >> 16) >= mthr ? 0xffff0000u : 0u);
+              wv[qd] &= keep;
+            }
+            w0_ = wv[0]; w1_ = wv[1]; w2_ = wv[2]; w3_ = wv[3];
+          }
+          st_shared_v4(sm + off, w0_, w1_, w2_, w3_);
+        }
+        fence_proxy_async_smem();      // generic-proxy writes -> visible to the tensor-core proxy
+        mbar_arrive(bar_masked(s));
+      }
     }
 
     // T group(s) out of TMEM -> (optional) global save -> scaled 16-bit operand(s) in smem
@@ -321,8 +402,9 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
       for (int c = 0; c < PCOLS / 16; ++c) {
         if (c >= BLOCK_N / 16 && (p.t_in != nullptr || !tap_touched(c - BLOCK_N / 16))) continue;
         uint32_t v[16];
-        tmem_ld16(lane_base + c * 16, v);
+        tmem_ld16(lane_base + c * 16, v);      // warp-collective: every lane takes part
         tmem_ld_wait();
+        if (!CONV && grow < 0) continue;       // rows past M hold zeros: nothing to add (the buffer row stays zero)
 #pragma unroll
         for (int w4 = 0; w4 < 4; ++w4)
           asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1,%2,%3,%4};"
@@ -533,12 +615,12 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
 }
 
 template <int BLOCK_N, int STAGES, typename OutT, bool CONV, int G, int MIN_CTAS = 1, bool DROP = false,
-          bool SPLITK = false>
+          bool SPLITK = false, bool BMASK = false>
 __global__ void __launch_bounds__(NUM_THREADS, MIN_CTAS)
 fused_lora_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmD, const __grid_constant__ CUtensorMap tmY,
                   const FusedParams p) {
-  fused_tile<BLOCK_N, STAGES, OutT, CONV, G, DROP, SPLITK>(tmX, tmW, tmD, tmY, p, blockIdx.x, blockIdx.y);
+  fused_tile<BLOCK_N, STAGES, OutT, CONV, G, DROP, SPLITK, BMASK>(tmX, tmW, tmD, tmY, p, blockIdx.x, blockIdx.y);
 }
 
 // Several same-dtype linear problems in ONE launch (sites that share an input: q/k/v of an

@@ -1,6 +1,7 @@
 // C-ABI entry point for the fused LoRA linear (forward and, on transposed operands, dX).
 // Replaces LoraInjectedLinear.forward (/root/reference/lora_diffusion/lora.py:53-58) and the dX
 // part of its autograd backward. Kernel: fused_core.cuh.
+#include <stdlib.h>
 #include "fused_core.cuh"
 #include "fused_persistent.cuh"
 #include "fused_splitk.cuh"
@@ -9,11 +10,12 @@
 
 namespace lb {
 
-template <int BLOCK_N, int STAGES, typename OutT, int MIN_CTAS, bool DROP = false, bool SPLITK = false>
+template <int BLOCK_N, int STAGES, typename OutT, int MIN_CTAS, bool DROP = false, bool SPLITK = false,
+          bool BMASK = false>
 static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, const FusedParams& p_in,
                          int out_dtype, cudaStream_t stream, int split = 1) {
-  using S = Smem<BLOCK_N, STAGES, OutT, 1, DROP>;
-  auto kern = fused_lora_kernel<BLOCK_N, STAGES, OutT, false, 1, MIN_CTAS, DROP, SPLITK>;
+  using S = Smem<BLOCK_N, STAGES, OutT, 1, DROP, BMASK>;
+  auto kern = fused_lora_kernel<BLOCK_N, STAGES, OutT, false, 1, MIN_CTAS, DROP, SPLITK, BMASK>;
   FusedParams p = p_in;
   p.split = 1;
   if constexpr (SPLITK) {
@@ -49,6 +51,21 @@ static SplitPlan plan_split(int M, int K, int N, int n_sms) {
   if (!splitk_enabled() || n_sms <= 0) return {0, 1};
   const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  {  // profiling knob: LB_SPLIT_FORCE=<s> [LB_SPLIT_BN=64|128] forces a split wherever it fits in one wave
+    static int force = -1, force_bn = 64;
+    if (force < 0) {
+      const char* e = getenv("LB_SPLIT_FORCE");
+      force = e ? atoi(e) : 0;
+      const char* b = getenv("LB_SPLIT_BN");
+      if (b && atoi(b) == 128) force_bn = 128;
+    }
+    if (force > 1) {
+      const long long tiles = static_cast<long long>(m_tiles) * ((N + force_bn - 1) / force_bn);
+      int sp = force < num_kb ? force : num_kb;
+      while (sp > 1 && tiles * sp > n_sms) --sp;
+      return sp > 1 ? SplitPlan{force_bn, sp} : SplitPlan{0, 1};
+    }
+  }
   SplitPlan best = {0, 1};
   double best_t = 1e30, base_t = 1e30;
   for (int bn = 64; bn <= 128; bn += 64) {
@@ -168,10 +185,11 @@ static int linear_fwd_impl(const void* X, const void* W, const float* bias,
                                   long long up_cs, const float* diag, float scale, void* Y,
                                   float* T_out, const float* T_in, int M, int K, int N, int r,
                                   int in_dtype, int out_dtype, float drop_p, const void* seed_dev,
-                                  void* stream) {
+                                  void* stream, int mask_input = 0) {
   using namespace lb;
   if (!(drop_p >= 0.f && drop_p < 1.f) || (drop_p > 0.f && (seed_dev == nullptr || T_in != nullptr)))
     return LB_ERR_SHAPE;
+  if (mask_input && !(drop_p > 0.f)) return LB_ERR_SHAPE;
   if (M <= 0 || N <= 0 || K <= 0) return LB_ERR_SHAPE;
   if (r < 1 || r > R_PAD) return LB_ERR_RANK;
   if (in_dtype != LB_BF16 && in_dtype != LB_F16) return LB_ERR_DTYPE;
@@ -191,6 +209,25 @@ static int linear_fwd_impl(const void* X, const void* W, const float* bias,
   p.drop_p = drop_p; p.drop_inv = 1.f / (1.f - drop_p);
   p.seed = reinterpret_cast<const unsigned long long*>(seed_dev);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (mask_input) {
+    // Dropout BACKWARD (dX): X = gY, and the T path must see mask o gY -- the epilogue warps write a
+    // masked copy of every A tile for the T MMA (fused_core.cuh, BMASK); mask index = row * K + k.
+    const SplitPlan spm = plan_split(M, K, N, sm_count());
+    if (spm.split > 1) {
+      if (out_dtype == LB_F32)
+        return spm.block_n == 64 ? launch_linear<64, 4, float, 1, false, true, true>(X, W, down16, Y, p, out_dtype, st, spm.split)
+                                 : launch_linear<128, 3, float, 1, false, true, true>(X, W, down16, Y, p, out_dtype, st, spm.split);
+      return spm.block_n == 64 ? launch_linear<64, 4, uint16_t, 1, false, true, true>(X, W, down16, Y, p, out_dtype, st, spm.split)
+                               : launch_linear<128, 3, uint16_t, 1, false, true, true>(X, W, down16, Y, p, out_dtype, st, spm.split);
+    }
+    const long long t128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
+    const bool nar = t128 < 90 && !(K >= 2048 && t128 >= 64);
+    if (out_dtype == LB_F32)
+      return nar ? launch_linear<64, 4, float, 1, false, false, true>(X, W, down16, Y, p, out_dtype, st)
+                 : launch_linear<128, 3, float, 1, false, false, true>(X, W, down16, Y, p, out_dtype, st);
+    return nar ? launch_linear<64, 4, uint16_t, 1, false, false, true>(X, W, down16, Y, p, out_dtype, st)
+               : launch_linear<128, 3, uint16_t, 1, false, false, true>(X, W, down16, Y, p, out_dtype, st);
+  }
   if (drop_p > 0.f) {
     // Dropout on the branch: the LoRA product keeps its own TMEM columns and is masked in the
     // drain (fused_core.cuh, DROP). One tile per CTA; BLOCK_N 64 (256 TMEM columns, 2 CTAs/SM)
@@ -293,6 +330,15 @@ extern "C" int lb_lora_linear_fwd_dropout(const void* X, const void* W, const fl
                                           int out_dtype, float drop_p, const void* seed_dev, void* stream) {
   return linear_fwd_impl(X, W, bias, down16, up, up_rs, up_cs, diag, scale, Y, T_out, nullptr, M, K, N, r,
                          in_dtype, out_dtype, drop_p, seed_dev, stream);
+}
+
+extern "C" int lb_lora_linear_dx_dropout(const void* gY, const void* Wt, const void* upT16, const float* down,
+                                         long long down_rs, long long down_cs, const float* diag, float scale,
+                                         void* dX, float* T_out, int M, int N_out, int K_in, int r,
+                                         int in_dtype, int out_dtype, float drop_p, const void* seed_dev,
+                                         void* stream) {
+  return linear_fwd_impl(gY, Wt, nullptr, upT16, down, down_rs, down_cs, diag, scale, dX, T_out, nullptr, M, N_out,
+                         K_in, r, in_dtype, out_dtype, drop_p, seed_dev, stream, 1);
 }
 
 extern "C" int lb_lora_linear_fwd_grouped(int n, const void* const* X, const void* const* W,

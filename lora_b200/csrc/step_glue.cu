@@ -43,7 +43,8 @@ prologue_kernel(const float* __restrict__ x0, const float* __restrict__ eps, con
   const long long obase = i * c_out;
   for (int c = 0; c < C; ++c) {
     const long long src = (static_cast<long long>(b) * C + c) * P + px;
-    st_any(out, obase + c, out_dt, a * x0[src] + s * eps[src]);
+    // two rounded products and one rounded sum, as torch evaluates add_noise (no FMA contraction)
+    st_any(out, obase + c, out_dt, __fadd_rn(__fmul_rn(a, x0[src]), __fmul_rn(s, eps[src])));
   }
   if (inp_mask) {
     st_any(out, obase + C, out_dt, inp_mask[static_cast<long long>(b) * P + px]);

@@ -8,9 +8,10 @@ The mask sits between the up-projection and the sum, so the branch cannot be acc
 base accumulator -- but it still never leaves the SM: the fused kernel gives the LoRA product
 T'.U^T its own TMEM columns and applies keep(m,n)/(1-p) while the tile is drained
 (lb_lora_linear_fwd_dropout / lb_lora_conv2d_fwd_dropout; csrc/fused_core.cuh, DROP): ONE launch,
-no extra pass over Y. Backward recomputes the same counter-based mask: dT = (mask o gY) . B
-(lb_lora_dropout_dt) is handed to the fused dX kernel as T_in, dB uses the masked reduction
-(lb_lora_wgrad_masked / lb_lora_wgrad_pair).
+no extra pass over Y. Backward recomputes the same counter-based mask INSIDE the dX kernel
+(lb_lora_linear_dx_dropout / lb_lora_conv2d_dx_dropout: the epilogue warps, idle during the K loop,
+write a masked copy of each gY tile that feeds only the rank-r MMA -- dT = (mask o gY) . B without a
+separate pass over gY); dB uses the masked reduction (lb_lora_wgrad_masked).
 
 The keep-mask is a hash of (per-call device seed, element index; csrc/dropmask.cuh) -- NOT ATen's Philox stream, so
 parity with the reference under dropout is distributional (keep probability, 1/(1-p) scaling,
@@ -94,10 +95,11 @@ class _LoraLinearDropoutFn(torch.autograd.Function):
         _, wt16 = st.frozen(lin.weight, cdt, need_t=True)
         upT16 = st.upT16(B, cdt)
         A32, B32 = _fp32_master(A), _fp32_master(B)
-        dTs = ops.dropout_dt(gy2d, B32, r, 1, ctx.p, seed, r)          # (mask o gY / (1-p)) . B
         dx_dtype = ctx.x_dtype if ctx.x_dtype in _LOW else torch.float32
-        dX, _ = ops.fused_linear(gy2d, wt16, None, upT16, A32, 1, K, ctx.diag, ctx.scale, r,
-                                 dx_dtype, False, t_in=dTs)
+        # one launch: the mask is applied to a shared-memory copy of each gY tile that feeds only the
+        # rank-r MMA; dTs = (mask o gY) . B WITHOUT the 1/(1-p) factor (folded into the scales below)
+        dX, dTs = ops.fused_linear_dx_dropout(gy2d, wt16, upT16, A32, ctx.diag, ctx.scale, r, dx_dtype, ctx.p, seed)
+        inv = 1.0 / (1.0 - ctx.p)
         need_x, need_a, need_b = ctx.needs_input_grad[:3]
         sink = st.grad_sink
         dA = dB = None
@@ -106,11 +108,9 @@ class _LoraLinearDropoutFn(torch.autograd.Function):
             tA = sink[0] if sink is not None else torch.zeros((r, K), device=gy.device, dtype=torch.float32)
         if need_b:
             tB = sink[1] if sink is not None else torch.zeros((N, r), device=gy.device, dtype=torch.float32)
-        if need_a and need_b:
-            ops.wgrad_pair(x2d, dTs, tA, gy2d, T, tB, ctx.diag, ctx.scale, r, ctx.p, seed, async_ok=sink is not None)
-        elif need_a:
-            ops.wgrad(x2d, dTs, ctx.diag, ctx.scale, tA, K, 1, r, async_ok=sink is not None)
-        elif need_b:
+        if need_a:
+            ops.wgrad(x2d, dTs, ctx.diag, ctx.scale * inv, tA, K, 1, r, async_ok=sink is not None)
+        if need_b:
             ops.wgrad_masked(gy2d, T, ctx.diag, ctx.scale, tB, 1, r, r, ctx.p, seed, async_ok=sink is not None)
         if sink is None:
             dA = tA.to(A.dtype).view_as(A) if need_a else None
@@ -168,17 +168,16 @@ class _LoraConv2dDropoutFn(torch.autograd.Function):
         _, w_b = _frozen_conv(st, conv.weight, cdt, True)
         upT16 = _upT16(st, B, cdt)
         A32, B32 = _fp32_master(A), _fp32_master(B)
-        dTs = ops.dropout_dt(gy2d, B32, r, 1, ctx.p, seed, r)
         dx_dtype = ctx.x_dtype if ctx.x_dtype in _LOW else torch.float32
-        dX, _ = ops.fused_conv2d(gy16, w_b, None, upT16, A32, taps - 1, taps, cin * taps, -1,
-                                 ctx.diag, ctx.scale, r, cin, kh, kw, kh - 1 - ph, kw - 1 - pw,
-                                 True, dx_dtype, False, t_in=dTs)
+        dX, dTs = ops.fused_conv2d_dx_dropout(gy16, w_b, upT16, A32, ctx.diag, ctx.scale, r, cin, kh, kw, ph, pw,
+                                              dx_dtype, ctx.p, seed)
+        inv = 1.0 / (1.0 - ctx.p)
         need_x, need_a, need_b = ctx.needs_input_grad[:3]
         sink = st.grad_sink
         dA = dB = None
         if need_a:
             tgt = sink[0] if sink is not None else torch.zeros((r, cin * taps), device=gy.device, dtype=torch.float32)
-            ops.wgrad_conv(x16, dTs, ctx.diag, ctx.scale, tgt, r, cin, h, w, kh, kw, ph, pw, async_ok=sink is not None)
+            ops.wgrad_conv(x16, dTs, ctx.diag, ctx.scale * inv, tgt, r, cin, h, w, kh, kw, ph, pw, async_ok=sink is not None)
             if sink is None:
                 dA = tgt.view_as(A).to(A.dtype)
         if need_b:

@@ -266,6 +266,44 @@ def wgrad_shift(S_rows: torch.Tensor, V: torch.Tensor, diag, scale: float, out: 
 
 
 # ------------------------------------------------------------------------------------ dropout
+def fused_linear_dx_dropout(gy2d: torch.Tensor, wt16: torch.Tensor, upT16: torch.Tensor, A32: torch.Tensor,
+                            diag, scale: float, r: int, out_dtype, p: float, seed: torch.Tensor):
+    """dX = gY.W + (((mask o gY).B) * scale*diag/(1-p)) . A  and  dTm = (mask o gY).B  (one launch)."""
+    _req_cuda(gy2d, wt16, upT16, A32, seed)
+    M, N_out = gy2d.shape
+    K_in = wt16.shape[0]
+    assert wt16.shape[1] == N_out and upT16.shape == (R_PAD, N_out) and gy2d.is_contiguous()
+    dX = torch.empty((M, K_in), device=gy2d.device, dtype=out_dtype)
+    dTm = torch.empty((M, R_PAD), device=gy2d.device, dtype=torch.float32)
+    check(_C.lib.lb_lora_linear_dx_dropout(ptr(gy2d), ptr(wt16), ptr(upT16), ptr(A32), 1, K_in, ptr(diag),
+                                           float(scale), ptr(dX), ptr(dTm), M, N_out, K_in, r,
+                                           dtype_code(gy2d.dtype), dtype_code(out_dtype), float(p), ptr(seed),
+                                           stream_ptr()), "lb_lora_linear_dx_dropout")
+    _count()
+    return dX, dTm
+
+
+def fused_conv2d_dx_dropout(gy_nhwc: torch.Tensor, w_b: torch.Tensor, upT16: torch.Tensor, A32: torch.Tensor,
+                            diag, scale: float, r: int, cin: int, kh: int, kw: int, ph: int, pw: int, out_dtype,
+                            p: float, seed: torch.Tensor):
+    """Conv analogue: dX (channels_last [N,cin,H,W]) and dTm [pixels,16] = (mask o gY).B, one launch."""
+    _req_cuda(gy_nhwc, w_b, upT16, A32, seed)
+    n, cout, h, w = gy_nhwc.shape
+    taps = kh * kw
+    assert gy_nhwc.is_contiguous(memory_format=torch.channels_last)
+    dX = torch.empty((n, cin, h, w), device=gy_nhwc.device, dtype=out_dtype, memory_format=torch.channels_last)
+    dTm = torch.empty((n * h * w, R_PAD), device=gy_nhwc.device, dtype=torch.float32)
+    import ctypes
+    down_ptr = ctypes.c_void_p(A32.data_ptr() + 4 * (taps - 1))       # A read flipped: last tap first
+    check(_C.lib.lb_lora_conv2d_dx_dropout(ptr(gy_nhwc), ptr(w_b), ptr(upT16), down_ptr, taps, cin * taps, -1,
+                                           ptr(diag), float(scale), ptr(dX), ptr(dTm), n, h, w, cout, cin, kh, kw,
+                                           kh - 1 - ph, kw - 1 - pw, r, dtype_code(gy_nhwc.dtype),
+                                           dtype_code(out_dtype), float(p), ptr(seed), stream_ptr()),
+          "lb_lora_conv2d_dx_dropout")
+    _count()
+    return dX, dTm
+
+
 def up_dropout_(y2d: torch.Tensor, T: torch.Tensor, up: torch.Tensor, up_rs: int, up_cs: int,
                 diag, scale: float, p: float, seed: torch.Tensor, r: int):
     """y2d[m,n] += scale/(1-p) * keep(m,n) * sum_j T[m,j] diag[j] up[n,j]   (in place)."""

@@ -30,6 +30,9 @@ SITES = [
     ("mid attn q/k/v/o", 64, 1280, 1280, 4), ("mid GEGLU", 64, 1280, 10240, 4), ("CLIP k/v/q/out", 77, 768, 768, 4),
 ]
 REPS = int(os.environ.get("REPS", 5))
+if os.environ.get("SITES") == "small":          # the <= 148-tile sites (split-K planner experiments)
+    SITES = [s for s in SITES if s[1] <= 256]
+TAG = os.environ.get("TAG", "")
 
 
 def run():
@@ -64,7 +67,7 @@ def run():
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(plan, open(os.path.join(ROOT, "gpurun_out", "sites_plan.json"), "w"), indent=1)
+    json.dump(plan, open(os.path.join(ROOT, "gpurun_out", f"sites_plan{TAG}.json"), "w"), indent=1)
 
 
 def summarize(csv_path, plan_path):
