@@ -530,86 +530,83 @@ tall_transform_kernel(const MatDesc* __restrict__ mats, const TItem* __restrict_
 }
 
 // ------------------------------------------------------------------------------------ Jacobi
-// One CTA (256 threads) per symmetric 32x32 matrix: cyclic Jacobi, round-robin ordering; the 16
-// disjoint rotations of a step are applied in parallel: thread = (rotation k = tid/16, index
-// tid%16 and +16). Outputs eigenvectors (columns, descending eigenvalue) and sqrt(max(eig, 0)).
+// One CTA (256 threads) per symmetric 32x32 matrix: cyclic two-sided Jacobi, round-robin ordering.
+// A step applies 16 disjoint rotations J = diag(J_0..J_15); A <- J^T A J decomposes into 16 x 16
+// independent 2x2 blocks {p_k,q_k} x {p_l,q_l}, ONE PER THREAD (k = tid / 16 rotates the block's
+// rows, l = tid % 16 its columns), so a step is: read (block + the two rotations' pivots) ->
+// barrier -> write -> barrier. Every thread derives its two rotations itself (no serial 16-thread
+// phase) and the round-robin pairing is closed-form (no permutation array): 2 barriers per step
+// instead of 5 (round 2a: 130-240 us per solve, latency-bound on the barriers).
+// Outputs eigenvectors (columns, descending eigenvalue) and sqrt(max(eig, 0)).
+__device__ __forceinline__ int rr_elem(int pos, int step) {   // element at tournament position `pos` after `step` rotations
+  if (pos == 0) return 0;
+  int e = (pos - 1 - step) % (L - 1);
+  if (e < 0) e += L - 1;
+  return e + 1;
+}
+__device__ __forceinline__ void jacobi_rot(float app, float aqq, float apq, float& c, float& s) {
+  c = 1.f; s = 0.f;
+  if (fabsf(apq) > 1e-30f) {
+    const float tau = (aqq - app) / (2.f * apq);
+    const float tt = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
+    c = rsqrtf(1.f + tt * tt);
+    s = tt * c;
+  }
+}
 __global__ void __launch_bounds__(256)
 jacobi32_kernel(const float* __restrict__ G, float* __restrict__ V, float* __restrict__ sigma, int sweeps,
                 float tol) {
   __shared__ float A[L][L + 1];
   __shared__ float Q[L][L + 1];
-  __shared__ int perm[L];
-  __shared__ float cs[16], sn[16];
-  __shared__ int pp[16], qq[16];
+  __shared__ float wmax[8];
   const int b = blockIdx.x, tid = threadIdx.x;
   const float* g = G + static_cast<size_t>(b) * L * L;
   for (int i = tid; i < L * L; i += 256) {
     A[i >> 5][i & 31] = g[i];
     Q[i >> 5][i & 31] = ((i >> 5) == (i & 31)) ? 1.f : 0.f;
   }
-  if (tid < L) perm[tid] = tid;
   __syncthreads();
-  const int k = tid >> 4, idx = tid & 15;
-  __shared__ float off_max[2];     // largest relative off-diagonal seen in the current sweep (by parity)
-  if (tid < 2) off_max[tid] = 0.f;
-  __syncthreads();
+  const int k = tid >> 4, l = tid & 15;
   for (int sw = 0; sw < sweeps; ++sw) {
+    float seen = 0.f;       // largest relative off-diagonal this thread met in the sweep
     for (int step = 0; step < L - 1; ++step) {
-      if (tid < 16) {
-        int p = perm[tid], q = perm[L - 1 - tid];
-        if (p > q) { const int tmp = p; p = q; q = tmp; }
-        const float apq = A[p][q], app = A[p][p], aqq = A[q][q];
-        float c = 1.f, s = 0.f;
-        if (fabsf(apq) > 1e-30f) {
-          const float tau = (aqq - app) / (2.f * apq);
-          const float tt = (tau >= 0.f ? 1.f : -1.f) / (fabsf(tau) + sqrtf(1.f + tau * tau));
-          c = rsqrtf(1.f + tt * tt);
-          s = tt * c;
-        }
-        cs[tid] = c; sn[tid] = s; pp[tid] = p; qq[tid] = q;
-        float rel = fabsf(apq) * rsqrtf(fmaxf(fabsf(app * aqq), 1e-37f));
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) rel = fmaxf(rel, __shfl_xor_sync(0x0000ffffu, rel, o));
-        if (tid == 0) off_max[sw & 1] = fmaxf(off_max[sw & 1], rel);
-      }
-      __syncthreads();
+      int pk = rr_elem(k, step), qk = rr_elem(L - 1 - k, step);
+      if (pk > qk) { const int t = pk; pk = qk; qk = t; }
+      int pl = rr_elem(l, step), ql = rr_elem(L - 1 - l, step);
+      if (pl > ql) { const int t = pl; pl = ql; ql = t; }
+      float ck, sk, cl, sl;
       {
-        const int p = pp[k], q = qq[k];
-        const float c = cs[k], s = sn[k];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {          // columns p, q of A and of the eigenvector matrix
-          const int r = idx + 16 * h;
-          const float aip = A[r][p], aiq = A[r][q];
-          A[r][p] = c * aip - s * aiq;
-          A[r][q] = s * aip + c * aiq;
-          const float vip = Q[r][p], viq = Q[r][q];
-          Q[r][p] = c * vip - s * viq;
-          Q[r][q] = s * vip + c * viq;
-        }
+        const float apq = A[pk][qk], app = A[pk][pk], aqq = A[qk][qk];
+        jacobi_rot(app, aqq, apq, ck, sk);
+        seen = fmaxf(seen, fabsf(apq) * rsqrtf(fmaxf(fabsf(app * aqq), 1e-37f)));
       }
-      __syncthreads();
-      {
-        const int p = pp[k], q = qq[k];
-        const float c = cs[k], s = sn[k];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {          // rows p, q of A
-          const int col = idx + 16 * h;
-          const float apj = A[p][col], aqj = A[q][col];
-          A[p][col] = c * apj - s * aqj;
-          A[q][col] = s * apj + c * aqj;
-        }
-      }
-      int nxt = 0;
-      if (tid < L) nxt = (tid >= 1) ? perm[tid == 1 ? L - 1 : tid - 1] : perm[0];
-      __syncthreads();
-      if (tid < L) perm[tid] = nxt;
+      jacobi_rot(A[pl][pl], A[ql][ql], A[pl][ql], cl, sl);
+      const float a00 = A[pk][pl], a01 = A[pk][ql], a10 = A[qk][pl], a11 = A[qk][ql];
+      const float v0p = Q[k][pl], v0q = Q[k][ql], v1p = Q[k + 16][pl], v1q = Q[k + 16][ql];
+      __syncthreads();                       // every read of the old matrix is done
+      // columns (p_l, q_l) by J_l, then rows (p_k, q_k) by J_k^T
+      const float b00 = cl * a00 - sl * a01, b01 = sl * a00 + cl * a01;
+      const float b10 = cl * a10 - sl * a11, b11 = sl * a10 + cl * a11;
+      A[pk][pl] = ck * b00 - sk * b10;
+      A[pk][ql] = ck * b01 - sk * b11;
+      A[qk][pl] = sk * b00 + ck * b10;
+      A[qk][ql] = sk * b01 + ck * b11;
+      Q[k][pl] = cl * v0p - sl * v0q;
+      Q[k][ql] = sl * v0p + cl * v0q;
+      Q[k + 16][pl] = cl * v1p - sl * v1q;
+      Q[k + 16][ql] = sl * v1p + cl * v1q;
       __syncthreads();
     }
-    // converged: every off-diagonal met in this sweep was below fp32 resolution of its diagonal pair
-    const float seen = off_max[sw & 1];
-    if (tid == 0) off_max[(sw + 1) & 1] = 0.f;
+    // converged: every off-diagonal met in this sweep was below `tol` relative to its diagonal pair
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) seen = fmaxf(seen, __shfl_xor_sync(0xffffffffu, seen, o));
+    if ((tid & 31) == 0) wmax[tid >> 5] = seen;
     __syncthreads();
-    if (seen < tol) break;
+    float all = wmax[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) all = fmaxf(all, wmax[w]);
+    __syncthreads();
+    if (all < tol) break;
   }
   if (tid < L) {
     const float w = A[tid][tid];

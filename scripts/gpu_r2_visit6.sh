@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 L=gpurun_out/v6.log
 : > $L
-for f in tests/test_dropout_gpu.py tests/test_step_ops_gpu.py tests/test_splitk_gpu.py; do
+for f in tests/test_svd_gpu.py tests/test_dropout_gpu.py tests/test_step_ops_gpu.py tests/test_splitk_gpu.py; do
   echo "=== $f" >> $L
   timeout 900 python -m pytest $f -q -x --timeout 600 -p no:cacheprovider 2>&1 | tail -12 >> $L
 done
@@ -17,6 +17,8 @@ for F in 0 2 3 4 6; do
   python scripts/prof_sites_ncu.py --summarize gpurun_out/sites_f$F.csv gpurun_out/sites_plan_f$F.json > gpurun_out/site_table_f$F.md 2>> $L
   cut -d'|' -f2-9 gpurun_out/site_table_f$F.md | head -30 >> $L
 done
+echo "=== bench svd" >> $L
+timeout 600 python scripts/bench_svd.py >> $L 2>&1
 echo "=== bench extended" >> $L
 timeout 900 python bench.py --extended --rank 8 --steps 20 --warmup 3 > gpurun_out/v6_bench_ext.json 2>> $L
 cut -c1-400 gpurun_out/v6_bench_ext.json >> $L
