@@ -29,6 +29,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -184,7 +185,7 @@ __device__ __forceinline__ void issue_tile(uint32_t raw, int slot, const MatDesc
   cp_async_commit();
 }
 // raw slot -> (W_tuned - W_base) split into bf16 hi / lo tiles in the swizzled MMA layout
-template <typename WT>
+template <typename WT, bool LO = true>
 __device__ __forceinline__ void convert_tile(uint32_t raw, int slot, uint32_t s_hi, uint32_t s_lo) {
   constexpr int KT = WTraits<WT>::KT;
   const int c = threadIdx.x & 7;
@@ -201,7 +202,8 @@ __device__ __forceinline__ void convert_tile(uint32_t raw, int slot, uint32_t s_
       for (int q = 0; q < 4; ++q) split2(d[2 * q], d[2 * q + 1], h[q], l[q]);
       const uint32_t off = tile_off<KT>(r, c);
       asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+      if constexpr (LO)
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
     } else {
       float d[4];
       WTraits<WT>::diff(t, b, d);
@@ -210,12 +212,14 @@ __device__ __forceinline__ void convert_tile(uint32_t raw, int slot, uint32_t s_
       split2(d[2], d[3], h[1], l[1]);
       const uint32_t off = tile_off<KT>(r, c >> 1) + (c & 1) * 8;    // 4 fp32 = half a 16-byte bf16 chunk
       asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(s_hi + off), "r"(h[0]), "r"(h[1]) : "memory");
-      asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(s_lo + off), "r"(l[0]), "r"(l[1]) : "memory");
+      if constexpr (LO)
+        asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(s_lo + off), "r"(l[0]), "r"(l[1]) : "memory");
     }
   }
 }
 
 // 8 consecutive fp32 of one row of a [rows, 32] tall-skinny operand -> one 16-byte chunk (hi, lo)
+template <bool LO = true>
 __device__ __forceinline__ void store_tall8(const float4& a, const float4& b, uint32_t s_hi, uint32_t s_lo,
                                             int row, int chunk) {
   uint32_t h[4], l[4];
@@ -223,13 +227,18 @@ __device__ __forceinline__ void store_tall8(const float4& a, const float4& b, ui
   split2(b.x, b.y, h[2], l[2]); split2(b.z, b.w, h[3], l[3]);
   const uint32_t off = tile_off<32>(row, chunk);
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_hi + off), "r"(h[0]), "r"(h[1]), "r"(h[2]), "r"(h[3]) : "memory");
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
+  if constexpr (LO)
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s_lo + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
 }
 
 // ------------------------------------------------------------------------------------ Y = dW . Z
 // CTA = one 128-row block of one matrix, K walked in KT-column steps. Warp w owns rows
 // [16w, 16w+16) x all 32 columns (4 n8 tiles). Optional fused Gram of the output tile.
-template <typename WT>
+// TERMS = how many of the split products are accumulated: 3 = hi.hi + lo.hi + hi.lo (fp32-faithful),
+// 2 = hi.hi + lo.hi (dW exact, the tall operand rounded to bf16: exact for the +-1 probes, and a
+// product with a rounded operand still lies in range(dW), which is what the basis needs),
+// 1 = hi.hi (bf16 product: only ever for an intermediate power-iteration pass).
+template <typename WT, int TERMS>
 __global__ void __launch_bounds__(THREADS, 2)
 mul_right_kernel(const MatDesc* __restrict__ mats, const RItem* __restrict__ items,
                  const float* __restrict__ Zin, float* __restrict__ Yout, float* __restrict__ G) {
@@ -274,8 +283,8 @@ mul_right_kernel(const MatDesc* __restrict__ mats, const RItem* __restrict__ ite
       cp_async_wait<0>();
     }
     __syncthreads();                                   // previous step's MMAs have read the operand tiles
-    convert_tile<WT>(raw, step & 1, s_hi, s_lo);
-    if (zr < KT) store_tall8(zv[0], zv[1], z_hi, z_lo, zr, zc);
+    convert_tile<WT, (TERMS >= 2)>(raw, step & 1, s_hi, s_lo);
+    if (zr < KT) store_tall8<(TERMS == 3)>(zv[0], zv[1], z_hi, z_lo, zr, zc);
     __syncthreads();
     if (step + 1 < nsteps) load_z((step + 1) * KT, zv);
 #pragma unroll
@@ -283,19 +292,19 @@ mul_right_kernel(const MatDesc* __restrict__ mats, const RItem* __restrict__ ite
       uint32_t ah[4], al[4];
       const uint32_t a_off = tile_off<KT>(warp * 16 + (lane & 15), ks * 2 + (lane >> 4));
       ldsm_x4(s_hi + a_off, ah);
-      ldsm_x4(s_lo + a_off, al);
+      if constexpr (TERMS >= 2) ldsm_x4(s_lo + a_off, al);
 #pragma unroll
       for (int np = 0; np < 2; ++np) {
         uint32_t bh[4], bl[4];
         const uint32_t b_off = tile_off<32>(ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), np * 2 + (lane >> 4));
         ldsm_x4_t(z_hi + b_off, bh);
-        ldsm_x4_t(z_lo + b_off, bl);
+        if constexpr (TERMS == 3) ldsm_x4_t(z_lo + b_off, bl);
         mma_bf16(acc[2 * np], ah, bh[0], bh[1]);
-        mma_bf16(acc[2 * np], al, bh[0], bh[1]);
-        mma_bf16(acc[2 * np], ah, bl[0], bl[1]);
+        if constexpr (TERMS >= 2) mma_bf16(acc[2 * np], al, bh[0], bh[1]);
+        if constexpr (TERMS == 3) mma_bf16(acc[2 * np], ah, bl[0], bl[1]);
         mma_bf16(acc[2 * np + 1], ah, bh[2], bh[3]);
-        mma_bf16(acc[2 * np + 1], al, bh[2], bh[3]);
-        mma_bf16(acc[2 * np + 1], ah, bl[2], bl[3]);
+        if constexpr (TERMS >= 2) mma_bf16(acc[2 * np + 1], al, bh[2], bh[3]);
+        if constexpr (TERMS == 3) mma_bf16(acc[2 * np + 1], ah, bl[2], bl[3]);
       }
     }
   }
@@ -338,7 +347,7 @@ mul_right_kernel(const MatDesc* __restrict__ mats, const RItem* __restrict__ ite
 // (Q^T)[32 x n] . dW[n x KT] (A = Q^T through ldmatrix.trans of the [n][32] chunk, B = the weight
 // tile through ldmatrix.trans) and adds it into Z[k][col] with fp32 atomics (Z zeroed beforehand).
 // Warp w: m16 tile (w & 1) of the 32 Q-columns, n8 tiles [(w>>1)*NT, +NT) of the KT weight columns.
-template <typename WT>
+template <typename WT, int TERMS>
 __global__ void __launch_bounds__(THREADS, 2)
 mul_left_kernel(const MatDesc* __restrict__ mats, const LItem* __restrict__ items,
                 const float* __restrict__ Qin, float* __restrict__ Zout) {
@@ -383,9 +392,9 @@ mul_left_kernel(const MatDesc* __restrict__ mats, const LItem* __restrict__ item
       cp_async_wait<0>();
     }
     __syncthreads();
-    convert_tile<WT>(raw, step & 1, s_hi, s_lo);
-    store_tall8(qv[0], qv[1], q_hi, q_lo, row, half * 2);
-    store_tall8(qv[2], qv[3], q_hi, q_lo, row, half * 2 + 1);
+    convert_tile<WT, (TERMS >= 2)>(raw, step & 1, s_hi, s_lo);
+    store_tall8<(TERMS == 3)>(qv[0], qv[1], q_hi, q_lo, row, half * 2);
+    store_tall8<(TERMS == 3)>(qv[2], qv[3], q_hi, q_lo, row, half * 2 + 1);
     __syncthreads();
     if (step + 1 < nsteps) load_q(it.n0 + (step + 1) * TM, qv);
 #pragma unroll
@@ -395,26 +404,26 @@ mul_left_kernel(const MatDesc* __restrict__ mats, const LItem* __restrict__ item
       uint32_t ah[4], al[4];
       const uint32_t a_off = tile_off<32>(ks * 16 + (lane >> 4) * 8 + (lane & 7), mt * 2 + ((lane >> 3) & 1));
       ldsm_x4_t(q_hi + a_off, ah);
-      ldsm_x4_t(q_lo + a_off, al);
+      if constexpr (TERMS == 3) ldsm_x4_t(q_lo + a_off, al);     // tall operand's low half
       if constexpr (NT == 2) {
         uint32_t bh[4], bl[4];
         const uint32_t b_off = tile_off<KT>(ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), ng * 2 + (lane >> 4));
         ldsm_x4_t(s_hi + b_off, bh);
-        ldsm_x4_t(s_lo + b_off, bl);
+        if constexpr (TERMS >= 2) ldsm_x4_t(s_lo + b_off, bl);   // dW's low half
         mma_bf16(acc[0], ah, bh[0], bh[1]);
-        mma_bf16(acc[0], al, bh[0], bh[1]);
-        mma_bf16(acc[0], ah, bl[0], bl[1]);
+        if constexpr (TERMS == 3) mma_bf16(acc[0], al, bh[0], bh[1]);
+        if constexpr (TERMS >= 2) mma_bf16(acc[0], ah, bl[0], bl[1]);
         mma_bf16(acc[1], ah, bh[2], bh[3]);
-        mma_bf16(acc[1], al, bh[2], bh[3]);
-        mma_bf16(acc[1], ah, bl[2], bl[3]);
+        if constexpr (TERMS == 3) mma_bf16(acc[1], al, bh[2], bh[3]);
+        if constexpr (TERMS >= 2) mma_bf16(acc[1], ah, bl[2], bl[3]);
       } else {
         uint32_t bh[2], bl[2];
         const uint32_t b_off = tile_off<KT>(ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7), ng);
         ldsm_x2_t(s_hi + b_off, bh);
-        ldsm_x2_t(s_lo + b_off, bl);
+        if constexpr (TERMS >= 2) ldsm_x2_t(s_lo + b_off, bl);
         mma_bf16(acc[0], ah, bh[0], bh[1]);
-        mma_bf16(acc[0], al, bh[0], bh[1]);
-        mma_bf16(acc[0], ah, bl[0], bl[1]);
+        if constexpr (TERMS == 3) mma_bf16(acc[0], al, bh[0], bh[1]);
+        if constexpr (TERMS >= 2) mma_bf16(acc[0], ah, bl[0], bl[1]);
       }
     }
   }
@@ -862,29 +871,60 @@ extern "C" int lb_svd_truncated_batched(const void* const* Wt, const void* const
     if (dev < 0 || dev >= 64 || !((attr_done >> dev) & 1ull)) {
       const int big_r = 2 * RAW_STAGE_BYTES + 2 * TM * 64 * 2 + 2 * 64 * 64;
       const int big_l = 2 * RAW_STAGE_BYTES + 2 * TM * 64 * 2 + 2 * TM * 64;
-      if (cudaFuncSetAttribute(mul_right_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_r) != cudaSuccess ||
-          cudaFuncSetAttribute(mul_right_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_r) != cudaSuccess ||
-          cudaFuncSetAttribute(mul_right_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_r) != cudaSuccess ||
-          cudaFuncSetAttribute(mul_left_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_l) != cudaSuccess ||
-          cudaFuncSetAttribute(mul_left_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_l) != cudaSuccess ||
-          cudaFuncSetAttribute(mul_left_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, big_l) != cudaSuccess)
+      bool ok = true;
+      auto set_r = [&](auto kern) { ok = ok && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, big_r) == cudaSuccess; };
+      auto set_l = [&](auto kern) { ok = ok && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, big_l) == cudaSuccess; };
+      set_r(mul_right_kernel<__half, 1>); set_r(mul_right_kernel<__half, 2>); set_r(mul_right_kernel<__half, 3>);
+      set_r(mul_right_kernel<__nv_bfloat16, 1>); set_r(mul_right_kernel<__nv_bfloat16, 2>); set_r(mul_right_kernel<__nv_bfloat16, 3>);
+      set_r(mul_right_kernel<float, 1>); set_r(mul_right_kernel<float, 2>); set_r(mul_right_kernel<float, 3>);
+      set_l(mul_left_kernel<__half, 1>); set_l(mul_left_kernel<__half, 2>); set_l(mul_left_kernel<__half, 3>);
+      set_l(mul_left_kernel<__nv_bfloat16, 1>); set_l(mul_left_kernel<__nv_bfloat16, 2>); set_l(mul_left_kernel<__nv_bfloat16, 3>);
+      set_l(mul_left_kernel<float, 1>); set_l(mul_left_kernel<float, 2>); set_l(mul_left_kernel<float, 3>);
+      if (!ok)
         return LB_ERR_CUDA;
       if (dev >= 0 && dev < 64) attr_done |= 1ull << dev;
     }
   }
-  auto mul_right = [&](bool gram) -> bool {
+  // split terms per pass (see mul_right_kernel): pass 1 multiplies by +-1 probes (exact in bf16), the
+  // power-iteration passes only shape a basis that is re-orthonormalised anyway and whose columns stay
+  // in range(dW) / range(dW^T) because dW itself keeps both halves; the LAST pass (B^T = dW^T Q, which
+  // the factors are read from) is fp32-faithful. LB_SVD_TERMS=3333 restores three terms everywhere.
+  static int terms_cfg[4] = {0, 0, 0, 0};
+  if (terms_cfg[0] == 0) {
+    const char* e = getenv("LB_SVD_TERMS");
+    const char* d = (e && e[0] && e[1] && e[2] && e[3]) ? e : "2223";
+    int tmp[4];
+    for (int i = 0; i < 4; ++i) tmp[i] = (d[i] >= '1' && d[i] <= '3') ? d[i] - '0' : 3;
+    tmp[3] = 3;
+    for (int i = 3; i >= 0; --i) terms_cfg[i] = tmp[i];
+  }
+  auto mul_right = [&](bool gram, int terms) -> bool {
     if (gram && cudaMemsetAsync(G, 0, g_bytes, st) != cudaSuccess) return false;
     float* g = gram ? G : nullptr;
-    if (w_dtype == LB_F16) mul_right_kernel<__half><<<nR, THREADS, smem_r, st>>>(mats, ritems, Z, Y, g);
-    else if (w_dtype == LB_BF16) mul_right_kernel<__nv_bfloat16><<<nR, THREADS, smem_r, st>>>(mats, ritems, Z, Y, g);
-    else mul_right_kernel<float><<<nR, THREADS, smem_r, st>>>(mats, ritems, Z, Y, g);
+#define LB_MR(WT_)                                                                                         \
+    do {                                                                                                   \
+      if (terms == 1) mul_right_kernel<WT_, 1><<<nR, THREADS, smem_r, st>>>(mats, ritems, Z, Y, g);        \
+      else if (terms == 2) mul_right_kernel<WT_, 2><<<nR, THREADS, smem_r, st>>>(mats, ritems, Z, Y, g);   \
+      else mul_right_kernel<WT_, 3><<<nR, THREADS, smem_r, st>>>(mats, ritems, Z, Y, g);                   \
+    } while (0)
+    if (w_dtype == LB_F16) LB_MR(__half);
+    else if (w_dtype == LB_BF16) LB_MR(__nv_bfloat16);
+    else LB_MR(float);
+#undef LB_MR
     return cudaGetLastError() == cudaSuccess;
   };
-  auto mul_left = [&]() -> bool {
+  auto mul_left = [&](int terms) -> bool {
     if (cudaMemsetAsync(Z, 0, static_cast<size_t>(p.sumK) * L * 4, st) != cudaSuccess) return false;
-    if (w_dtype == LB_F16) mul_left_kernel<__half><<<nL, THREADS, smem_l, st>>>(mats, litems, Y, Z);
-    else if (w_dtype == LB_BF16) mul_left_kernel<__nv_bfloat16><<<nL, THREADS, smem_l, st>>>(mats, litems, Y, Z);
-    else mul_left_kernel<float><<<nL, THREADS, smem_l, st>>>(mats, litems, Y, Z);
+#define LB_ML(WT_)                                                                                     \
+    do {                                                                                               \
+      if (terms == 1) mul_left_kernel<WT_, 1><<<nL, THREADS, smem_l, st>>>(mats, litems, Y, Z);        \
+      else if (terms == 2) mul_left_kernel<WT_, 2><<<nL, THREADS, smem_l, st>>>(mats, litems, Y, Z);   \
+      else mul_left_kernel<WT_, 3><<<nL, THREADS, smem_l, st>>>(mats, litems, Y, Z);                   \
+    } while (0)
+    if (w_dtype == LB_F16) LB_ML(__half);
+    else if (w_dtype == LB_BF16) LB_ML(__nv_bfloat16);
+    else LB_ML(float);
+#undef LB_ML
     return cudaGetLastError() == cudaSuccess;
   };
   // orth(buf): [Gram given in G] -> Jacobi -> buf <- buf V diag(1/s) (+ Gram of the result)
@@ -903,16 +943,16 @@ extern "C" int lb_svd_truncated_batched(const void* const* Wt, const void* const
 
   probes_kernel<<<static_cast<int>((p.sumK + 255) / 256), 256, 0, st>>>(Z, p.sumK, seed);
   LB_SVD_CHECK();
-  if (!mul_right(true)) return LB_ERR_CUDA;                       // Y = dW Om, G = Y^T Y
+  if (!mul_right(true, terms_cfg[0])) return LB_ERR_CUDA;         // Y = dW Om, G = Y^T Y
   for (int it = 0; it < power_iters; ++it) {
     if (!jacobi(6, 1e-4f) || !transform(0, true, false)) return LB_ERR_CUDA;    // Y <- orth(Y)
-    if (!mul_left()) return LB_ERR_CUDA;                                   // Z = dW^T Y
+    if (!mul_left(terms_cfg[1])) return LB_ERR_CUDA;                       // Z = dW^T Y
     if (!transform(1, false, true) || !jacobi(6, 1e-4f) || !transform(1, true, false)) return LB_ERR_CUDA;   // Z <- orth(Z)
-    if (!mul_right(true)) return LB_ERR_CUDA;                              // Y = dW Z, G
+    if (!mul_right(true, terms_cfg[2])) return LB_ERR_CUDA;                // Y = dW Z, G
   }
   // Q = orth2(Y): the basis the projected problem is solved in must be orthonormal to fp32 accuracy
   if (!jacobi(6, 1e-4f) || !transform(0, true, true) || !jacobi(8, 1e-7f) || !transform(0, true, false)) return LB_ERR_CUDA;
-  if (!mul_left()) return LB_ERR_CUDA;                                     // B^T = dW^T Q
+  if (!mul_left(3)) return LB_ERR_CUDA;                                    // B^T = dW^T Q (fp32-faithful)
   if (!transform(1, false, true) || !jacobi(10, 1e-7f)) return LB_ERR_CUDA;       // B B^T = Uh diag(s^2) Uh^T
   factors_kernel<<<nTy, THREADS, 0, st>>>(mats, ty, 0, Y, V, sig, rank, out);
   LB_SVD_CHECK();
