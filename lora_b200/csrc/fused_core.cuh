@@ -61,6 +61,10 @@ struct FusedParams {
   // tile's [128][BLOCK_N + 16 G] fp32 buffer in `ws` with vector reductions at L2; `counters[tile]`
   // elects the last CTA to arrive, which reads the reduced row back in one burst, wipes it and runs
   // the ordinary epilogue. Buffer and counters must be zero on entry; the elected CTA leaves them so.
+  int a_rows;          // LINEAR, single row tile: rows of the X box actually loaded (multiple of 8, < 128);
+                       // 0 = the full 128-row box. Rows past it are never written in shared memory, so the
+                       // accumulator rows past M hold garbage -- they are never stored (Y/T_out clip at M,
+                       // the split-K reduction skips them)
   int split;
   float* ws;
   unsigned int* counters;
@@ -188,12 +192,14 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       LB_STAMP(1);                       // first TMA about to be issued
+      const uint32_t tx_bytes =
+          (!CONV && p.a_rows > 0) ? static_cast<uint32_t>(S::TX_BYTES - (BLOCK_M - p.a_rows) * BLOCK_K * 2) : S::TX_BYTES;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         const int it = kb - kb_begin;
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(bar_empty(s), ph ^ 1);
-        mbar_expect_tx(bar_full(s), S::TX_BYTES);
+        mbar_expect_tx(bar_full(s), tx_bytes);
         const uint32_t sa = sbase + s * S::STAGE_BYTES;
         const uint32_t sb = sa + S::A_BYTES;
         if constexpr (CONV) {

@@ -10,6 +10,16 @@
 
 namespace lb {
 
+// Single-row-tile sites (M = 77 text tokens, 64 mid-block pixels): load only the rows that exist.
+// The TMA engine, not the tensor core, paces these kernels (~2.5 clk per 128-byte box row), and rows
+// past M are pure zero fill. LB_FULL_BOX=1 restores the 128-row box (profiling).
+static int tight_rows(int M) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("LB_FULL_BOX"); off = (e && e[0] == '1') ? 1 : 0; }
+  if (off || M > BLOCK_M - 8) return 0;
+  return (M + 7) & ~7;
+}
+
 template <int BLOCK_N, int STAGES, typename OutT, int MIN_CTAS, bool DROP = false, bool SPLITK = false,
           bool BMASK = false>
 static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, const FusedParams& p_in,
@@ -31,7 +41,8 @@ static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, 
   const CUtensorMapDataType in_dt = p.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
   CUtensorMap tmX, tmW, tmD, tmY;
-  if (!tmap_2d(&tmX, X, in_dt, 2, p.K, p.M, BLOCK_K, BLOCK_M, true)) return LB_ERR_TMAP;
+  p.a_rows = tight_rows(p.M);
+  if (!tmap_2d(&tmX, X, in_dt, 2, p.K, p.M, BLOCK_K, p.a_rows ? p.a_rows : BLOCK_M, true)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmW, W, in_dt, 2, p.K, p.N, BLOCK_K, BLOCK_N, true)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmD, Dn, in_dt, 2, p.K, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmY, Y, out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
@@ -118,8 +129,9 @@ static int launch_grouped(GroupedArgs& a, const void* const* X, const void* cons
   const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
   int total = 0;
   for (int i = 0; i < a.n_problems; ++i) {
-    const FusedParams& p = a.p[i];
-    if (!tmap_2d(&a.tmX[i], X[i], in_dt, 2, p.K, p.M, BLOCK_K, BLOCK_M, true)) return LB_ERR_TMAP;
+    FusedParams& p = a.p[i];
+    p.a_rows = tight_rows(p.M);
+    if (!tmap_2d(&a.tmX[i], X[i], in_dt, 2, p.K, p.M, BLOCK_K, p.a_rows ? p.a_rows : BLOCK_M, true)) return LB_ERR_TMAP;
     if (!tmap_2d(&a.tmW[i], W[i], in_dt, 2, p.K, p.N, BLOCK_K, BLOCK_N, true)) return LB_ERR_TMAP;
     if (!tmap_2d(&a.tmD[i], Dn[i], in_dt, 2, p.K, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
     if (!tmap_2d(&a.tmY[i], Y[i], out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
