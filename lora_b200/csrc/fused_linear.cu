@@ -173,7 +173,7 @@ static unsigned long long* g_dbg = nullptr;  // profiling: device buffer of 16 t
 extern "C" int lb_debug_set_linear_mode(int mode) {
   // schedule (0 auto, 1 one tile per CTA, 2 persistent, 3 EXPERIMENTAL cluster split-K)
   // + 4 * block_n choice (0 auto, 1: 64, 2: 128) + 16 * split-K factor choice (0: auto, 1..3: 2..4 CTAs)
-  if (mode < 0 || mode > 63 || ((mode >> 2) & 3) == 3) return LB_ERR_SHAPE;
+  if (mode < 0 || mode > 63) return LB_ERR_SHAPE;          // block_n choice 3 = 192 (16-bit outputs, one tile per CTA)
   lb::g_linear_mode = mode;
   return LB_OK;
 }
@@ -300,6 +300,8 @@ static int linear_fwd_impl(const void* X, const void* W, const float* bias,
       return launch_splitk<64, 3, uint16_t, 4>(X, W, down16, Y, p, out_dtype, st);
     }
   }
+  if (bn_choice == 3 && out_dtype != LB_F32)
+    return launch_linear<192, 4, uint16_t, 1>(X, W, down16, Y, p, out_dtype, st);
   const bool persistent = sched == 2 || (sched == 0 && tiles_n >= 3 * 148);
   if (persistent) {
     if (out_dtype == LB_F32) {

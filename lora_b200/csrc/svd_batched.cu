@@ -542,10 +542,11 @@ tall_transform_kernel(const MatDesc* __restrict__ mats, const TItem* __restrict_
 // One CTA (256 threads) per symmetric 32x32 matrix: cyclic two-sided Jacobi, round-robin ordering.
 // A step applies 16 disjoint rotations J = diag(J_0..J_15); A <- J^T A J decomposes into 16 x 16
 // independent 2x2 blocks {p_k,q_k} x {p_l,q_l}, ONE PER THREAD (k = tid / 16 rotates the block's
-// rows, l = tid % 16 its columns), so a step is: read (block + the two rotations' pivots) ->
-// barrier -> write -> barrier. Every thread derives its two rotations itself (no serial 16-thread
-// phase) and the round-robin pairing is closed-form (no permutation array): 2 barriers per step
-// instead of 5 (round 2a: 130-240 us per solve, latency-bound on the barriers).
+// rows, l = tid % 16 its columns), so a step is: read (block + the column rotation's pivots) ->
+// barrier -> write -> barrier. Every lane derives the rotation of its column pair and fetches the
+// row pair's from a lane of its own warp (no serial 16-thread phase); the round-robin pairing is
+// tabulated once (no permutation array to maintain): 2 barriers per step instead of 5 (round 2a:
+// 130-240 us per solve, latency-bound on the barriers).
 // Outputs eigenvectors (columns, descending eigenvalue) and sqrt(max(eig, 0)).
 __device__ __forceinline__ int rr_elem(int pos, int step) {   // element at tournament position `pos` after `step` rotations
   if (pos == 0) return 0;
@@ -568,28 +569,38 @@ jacobi32_kernel(const float* __restrict__ G, float* __restrict__ V, float* __res
   __shared__ float A[L][L + 1];
   __shared__ float Q[L][L + 1];
   __shared__ float wmax[8];
+  __shared__ unsigned char pair_p[L - 1][16], pair_q[L - 1][16];   // the tournament, tabulated once
   const int b = blockIdx.x, tid = threadIdx.x;
   const float* g = G + static_cast<size_t>(b) * L * L;
   for (int i = tid; i < L * L; i += 256) {
     A[i >> 5][i & 31] = g[i];
     Q[i >> 5][i & 31] = ((i >> 5) == (i & 31)) ? 1.f : 0.f;
   }
+  for (int i = tid; i < (L - 1) * 16; i += 256) {
+    const int step = i >> 4, kk = i & 15;
+    int pp = rr_elem(kk, step), qq = rr_elem(L - 1 - kk, step);
+    if (pp > qq) { const int t = pp; pp = qq; qq = t; }
+    pair_p[step][kk] = static_cast<unsigned char>(pp);
+    pair_q[step][kk] = static_cast<unsigned char>(qq);
+  }
   __syncthreads();
+  // lane = (k & 1) * 16 + l: every lane derives the rotation of ITS COLUMN pair l; the row pair k's
+  // rotation is the one lane (k & 1) * 16 + k of the same warp derived (k < 16): two shuffles
   const int k = tid >> 4, l = tid & 15;
+  const int src_lane = (tid & 16) + k;
   for (int sw = 0; sw < sweeps; ++sw) {
     float seen = 0.f;       // largest relative off-diagonal this thread met in the sweep
     for (int step = 0; step < L - 1; ++step) {
-      int pk = rr_elem(k, step), qk = rr_elem(L - 1 - k, step);
-      if (pk > qk) { const int t = pk; pk = qk; qk = t; }
-      int pl = rr_elem(l, step), ql = rr_elem(L - 1 - l, step);
-      if (pl > ql) { const int t = pl; pl = ql; ql = t; }
-      float ck, sk, cl, sl;
+      const int pk = pair_p[step][k], qk = pair_q[step][k];
+      const int pl = pair_p[step][l], ql = pair_q[step][l];
+      float cl, sl;
       {
-        const float apq = A[pk][qk], app = A[pk][pk], aqq = A[qk][qk];
-        jacobi_rot(app, aqq, apq, ck, sk);
+        const float apq = A[pl][ql], app = A[pl][pl], aqq = A[ql][ql];
+        jacobi_rot(app, aqq, apq, cl, sl);
         seen = fmaxf(seen, fabsf(apq) * rsqrtf(fmaxf(fabsf(app * aqq), 1e-37f)));
       }
-      jacobi_rot(A[pl][pl], A[ql][ql], A[pl][ql], cl, sl);
+      const float ck = __shfl_sync(0xffffffffu, cl, src_lane);
+      const float sk = __shfl_sync(0xffffffffu, sl, src_lane);
       const float a00 = A[pk][pl], a01 = A[pk][ql], a10 = A[qk][pl], a11 = A[qk][ql];
       const float v0p = Q[k][pl], v0q = Q[k][ql], v1p = Q[k + 16][pl], v1q = Q[k + 16][ql];
       __syncthreads();                       // every read of the old matrix is done

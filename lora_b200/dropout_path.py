@@ -17,11 +17,15 @@ The keep-mask is a hash of (per-call device seed, element index; csrc/dropmask.c
 parity with the reference under dropout is distributional (keep probability, 1/(1-p) scaling,
 forward/backward mask consistency; tests/test_dropout_gpu.py), not bitwise.
 """
+import os
+
 import torch
 
 from . import ops
 from ._C import LoraB200Error
 from .modules import _LOW, _SiteState, _compute_dtype, _fp32_master, _out_dtype
+
+_TWO_PASS = os.environ.get("LB_DROPOUT_BWD", "") == "twopass"
 
 
 class _SeedPool:
@@ -98,8 +102,14 @@ class _LoraLinearDropoutFn(torch.autograd.Function):
         dx_dtype = ctx.x_dtype if ctx.x_dtype in _LOW else torch.float32
         # one launch: the mask is applied to a shared-memory copy of each gY tile that feeds only the
         # rank-r MMA; dTs = (mask o gY) . B WITHOUT the 1/(1-p) factor (folded into the scales below)
-        dX, dTs = ops.fused_linear_dx_dropout(gy2d, wt16, upT16, A32, ctx.diag, ctx.scale, r, dx_dtype, ctx.p, seed)
-        inv = 1.0 / (1.0 - ctx.p)
+        if _TWO_PASS:      # round-2a formulation, kept for same-box A/B timing: a masked pass over gY, then T_in
+            dTs = ops.dropout_dt(gy2d, B32, r, 1, ctx.p, seed, r)          # (mask o gY / (1-p)) . B
+            dX, _ = ops.fused_linear(gy2d, wt16, None, upT16, A32, 1, K, ctx.diag, ctx.scale, r,
+                                     dx_dtype, False, t_in=dTs)
+            inv = 1.0
+        else:
+            dX, dTs = ops.fused_linear_dx_dropout(gy2d, wt16, upT16, A32, ctx.diag, ctx.scale, r, dx_dtype, ctx.p, seed)
+            inv = 1.0 / (1.0 - ctx.p)
         need_x, need_a, need_b = ctx.needs_input_grad[:3]
         sink = st.grad_sink
         dA = dB = None
@@ -169,9 +179,16 @@ class _LoraConv2dDropoutFn(torch.autograd.Function):
         upT16 = _upT16(st, B, cdt)
         A32, B32 = _fp32_master(A), _fp32_master(B)
         dx_dtype = ctx.x_dtype if ctx.x_dtype in _LOW else torch.float32
-        dX, dTs = ops.fused_conv2d_dx_dropout(gy16, w_b, upT16, A32, ctx.diag, ctx.scale, r, cin, kh, kw, ph, pw,
-                                              dx_dtype, ctx.p, seed)
-        inv = 1.0 / (1.0 - ctx.p)
+        if _TWO_PASS:
+            dTs = ops.dropout_dt(gy2d, B32, r, 1, ctx.p, seed, r)
+            dX, _ = ops.fused_conv2d(gy16, w_b, None, upT16, A32, taps - 1, taps, cin * taps, -1,
+                                     ctx.diag, ctx.scale, r, cin, kh, kw, kh - 1 - ph, kw - 1 - pw,
+                                     True, dx_dtype, False, t_in=dTs)
+            inv = 1.0
+        else:
+            dX, dTs = ops.fused_conv2d_dx_dropout(gy16, w_b, upT16, A32, ctx.diag, ctx.scale, r, cin, kh, kw, ph, pw,
+                                                  dx_dtype, ctx.p, seed)
+            inv = 1.0 / (1.0 - ctx.p)
         need_x, need_a, need_b = ctx.needs_input_grad[:3]
         sink = st.grad_sink
         dA = dB = None

@@ -32,13 +32,19 @@ SITES = [
 REPS = int(os.environ.get("REPS", 5))
 if os.environ.get("SITES") == "small":          # the <= 148-tile sites (split-K planner experiments)
     SITES = [s for s in SITES if s[1] <= 256]
+if os.environ.get("SITES") == "geglu":          # the wide projections + the mid block (schedule experiments)
+    SITES = [s for s in SITES if "GEGLU" in s[0] or s[0].startswith("mid")]
 TAG = os.environ.get("TAG", "")
+MODE = int(os.environ.get("MODE", 0))           # lb_debug_set_linear_mode value (0 = the planner's choice)
 
 
 def run():
     import torch
     from lora_b200 import ops
     dev, dt = "cuda", torch.bfloat16
+    if MODE:
+        from lora_b200 import _C
+        assert _C.lib.lb_debug_set_linear_mode(MODE) == 0
     marker = torch.zeros(1, device=dev, dtype=torch.int64)
     plan = []
     cases = []

@@ -154,6 +154,21 @@ def test_backward_kernels_match_oracle(M, K, N, r):
     assert rel_err(dX, fdX) < 1e-2 and rel_err(dA, fdA) < 1e-2 and rel_err(dB, fdB) < 1e-2
 
 
+@pytest.mark.parametrize("M,K,N,r", [(256, 1280, 2304, 4), (64, 640, 1000, 8), (300, 320, 192, 4)])
+def test_block_n_192_schedule_matches_default(M, K, N, r):
+    """The 192-wide tile (13 TMEM-resident n8 groups, 3 store boxes; 16-bit outputs) is the same math."""
+    from lora_b200 import _C
+    x, W, A, B, b, d = make_case(M, K, N, r, torch.bfloat16, seed=M + N + r, diag=True)
+    try:
+        assert _C.lib.lb_debug_set_linear_mode(1 + 4 * 3) == 0
+        y, t, _ = run_fused(x, W, A, B, b, d, 0.9, torch.bfloat16)
+    finally:
+        _C.lib.lb_debug_set_linear_mode(0)
+    y0, t0, _ = run_fused(x, W, A, B, b, d, 0.9, torch.bfloat16)
+    assert rel_err(t, t0) < 3e-6
+    assert rel_err(y, y0) < 3e-3          # both rounded to bf16 once
+
+
 @pytest.mark.parametrize("mode", [1 + 4, 1 + 8, 2 + 4, 2 + 8])
 @pytest.mark.parametrize("M,K,N,r", SHAPES)
 def test_every_tile_schedule_gives_the_same_result(M, K, N, r, mode):
