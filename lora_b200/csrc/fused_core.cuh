@@ -222,6 +222,28 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
       const uint32_t idesc_wide = umma_idesc_f16(p.fmt, BLOCK_M, BLOCK_N + R_PAD);
       const uint32_t idesc_base = umma_idesc_f16(p.fmt, BLOCK_M, BLOCK_N);
       const uint32_t idesc_t = umma_idesc_f16(p.fmt, BLOCK_M, R_PAD);
+      // BMASK: T_tap += (mask o gY tile) . D^T from the masked copy the epilogue warps write next to
+      // each landed A tile (same swizzled layout). Issued ONE STAGE BEHIND the base MMAs, so the masking
+      // of stage i overlaps the base MMAs of stage i+1 instead of stalling the issue; the smem slot is
+      // released by the commit that follows its T MMAs.
+      auto issue_masked_t = [&](int itp) {
+        const int kbp = kb_begin + itp;
+        const int sp = itp % STAGES;
+        const uint32_t php = (itp / STAGES) & 1;
+        const int tapp = (G > 1) ? kbp / cblocks : 0;
+        const bool firstp = (G > 1) ? ((kbp - tapp * cblocks) == 0 || itp == 0) : (itp == 0);
+        mbar_wait(bar_masked(sp), php);
+        tc_fence_after();
+        const uint32_t sbp = sbase + sp * S::STAGE_BYTES + S::A_BYTES;
+        const uint32_t smp = sbp + S::B_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          const uint64_t amd = umma_smem_desc(smp + k * UMMA_K * 2, 16, 1024, 2);
+          const uint64_t dd = umma_smem_desc(sbp + BLOCK_N * 128 + k * UMMA_K * 2, 16, 1024, 2);
+          umma_f16_ss(tmem + BLOCK_N + R_PAD * tapp, amd, dd, idesc_t, !(firstp && k == 0));
+        }
+        umma_commit(bar_empty(sp));
+      };
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         const int it = kb - kb_begin;
         const int s = it % STAGES;
@@ -240,7 +262,7 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
           const uint64_t ad = umma_smem_desc(sa + k * UMMA_K * 2, 16, 1024, 2);
           const uint64_t bd = umma_smem_desc(sb + k * UMMA_K * 2, 16, 1024, 2);
           if constexpr (BMASK) {
-            umma_f16_ss(tmem, ad, bd, idesc_base, (it | k) != 0);       // base only; T below, from the masked tile
+            umma_f16_ss(tmem, ad, bd, idesc_base, (it | k) != 0);       // base only; T one stage behind
           } else if constexpr (G == 1) {
             umma_f16_ss(tmem, ad, bd, idesc_wide, (it | k) != 0);
           } else {
@@ -250,20 +272,13 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
           }
         }
         if constexpr (BMASK) {
-          // T_tap += (mask o gY tile) . D^T : the epilogue warps have written the masked copy of this
-          // stage's A tile next to it (same swizzled layout)
-          mbar_wait(bar_masked(s), ph);
-          tc_fence_after();
-          const uint32_t sm = sb + S::B_BYTES;
-          const bool first = (G > 1) ? tap_first : (it == 0);
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t amd = umma_smem_desc(sm + k * UMMA_K * 2, 16, 1024, 2);
-            const uint64_t dd = umma_smem_desc(sb + BLOCK_N * 128 + k * UMMA_K * 2, 16, 1024, 2);
-            umma_f16_ss(tmem + BLOCK_N + R_PAD * tap, amd, dd, idesc_t, !(first && k == 0));
-          }
+          if (it > 0) issue_masked_t(it - 1);
+        } else {
+          umma_commit(bar_empty(s));  // frees the smem slot when these MMAs retire
         }
-        umma_commit(bar_empty(s));  // frees the smem slot when these MMAs retire
+      }
+      if constexpr (BMASK) {
+        if (kb_end > kb_begin) issue_masked_t(kb_end - kb_begin - 1);
       }
       umma_commit(bar_acc);
       LB_STAMP(3);                         // all main-loop MMAs issued
