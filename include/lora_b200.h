@@ -34,6 +34,13 @@ enum lb_status {
 };
 
 enum lb_dtype { LB_BF16 = 0, LB_F16 = 1, LB_F32 = 2 };
+/* OR-ed into `in_dtype` of the fused linear entries: the frozen weight argument (W, or Wt of the dX
+ * entry) is NOT row-major [N, K] but the 64 x 64-block layout written by lb_tile_weight -- block
+ * (n64, kb) occupies rows [(n64 * ceil(K/64) + kb) * 64, +64) of a [rows, 64] 16-bit tensor, zero padded
+ * -- so that every TMA box of the weight stream is one contiguous 8 KB run of HBM (a row-major box is
+ * 64-192 rows of 128 bytes a whole K apart: one DRAM page activation per 128-256 bytes). The frozen
+ * weights are the cold, never-rewritten bulk of a step's traffic; their 16-bit copy is ours to lay out. */
+#define LB_W_TILED 0x100
 
 /* ABI version of this header (bumped on any signature change). */
 int lb_abi_version(void);
@@ -271,6 +278,14 @@ int lb_lora_merge(const void* W, int w_dtype, const float* up, const float* down
  * The fused kernels are then called with K := 3K; nothing else changes. */
 int lb_split_bf16x3(const float* src, long long src_rs, void* dst16, int R, int C, int pattern,
                     void* stream);
+
+/* Frozen-weight preparation for LB_W_TILED: the logical [N, K] operand, element (n, k) read from
+ * src[n*src_rs + k*src_cs] (W itself: src_rs = K, src_cs = 1; the dX operand W^T of a [N_out, K_in]
+ * weight: N = K_in, K = N_out, src_rs = 1, src_cs = K_in), cast to 16 bits and written as 64 x 64 blocks
+ * (see LB_W_TILED), zero padded. dst16 holds lb_tiled_weight_elems(N, K) elements, 16-byte aligned. */
+long long lb_tiled_weight_elems(int N, int K);
+int lb_tile_weight(const void* src, int src_dtype, long long src_rs, long long src_cs, int N, int K,
+                   void* dst16, int out_dtype, void* stream);
 
 /* Frozen-weight preparation: src [R,C] (LB_F32/LB_BF16/LB_F16) -> dst16 [R,C] and/or
  * dstT16 [C,R] (either may be NULL). One-time cost per frozen weight. */

@@ -61,15 +61,27 @@ struct FusedParams {
   // tile's [128][BLOCK_N + 16 G] fp32 buffer in `ws` with vector reductions at L2; `counters[tile]`
   // elects the last CTA to arrive, which reads the reduced row back in one burst, wipes it and runs
   // the ordinary epilogue. Buffer and counters must be zero on entry; the elected CTA leaves them so.
-  int a_rows;          // LINEAR, single row tile: rows of the X box actually loaded (multiple of 8, < 128);
-                       // 0 = the full 128-row box. Rows past it are never written in shared memory, so the
-                       // accumulator rows past M hold garbage -- they are never stored (Y/T_out clip at M,
-                       // the split-K reduction skips them)
+  int w_tiled;         // 1: the frozen weight is stored as 64 x 64 blocks, block (n64, kb) = rows
+                       // [(n64 * num_kb + kb) * 64, +64) of a [rows, 64] tensor (lb_tile_weight): every TMA box
+                       // is ONE contiguous 8 KB run of HBM instead of 64 rows a whole K apart
   int split;
   float* ws;
   unsigned int* counters;
   unsigned long long* dbg;  // profiling only: 16 x %globaltimer stamps written by CTA (0,0), or null
 };
+
+// B-operand tile of the frozen weight: rows [n0, n0 + BLOCK_N) x K block kb (global index, conv: tap-major).
+template <int BLOCK_N>
+__device__ __forceinline__ void load_w_tile(const CUtensorMap* tmW, uint32_t bar, uint32_t dst, int k_elem, int kb,
+                                            int num_kb, int n0, int w_tiled) {
+  if (w_tiled) {
+#pragma unroll
+    for (int j = 0; j < BLOCK_N / 64; ++j)
+      tma_load_2d(tmW, bar, dst + j * (64 * 128), 0, (((n0 >> 6) + j) * num_kb + kb) * 64);
+  } else {
+    tma_load_2d(tmW, bar, dst, k_elem, n0);
+  }
+}
 
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -192,26 +204,24 @@ __device__ __forceinline__ void fused_tile(const CUtensorMap& tmX, const CUtenso
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       LB_STAMP(1);                       // first TMA about to be issued
-      const uint32_t tx_bytes =
-          (!CONV && p.a_rows > 0) ? static_cast<uint32_t>(S::TX_BYTES - (BLOCK_M - p.a_rows) * BLOCK_K * 2) : S::TX_BYTES;
       for (int kb = kb_begin; kb < kb_end; ++kb) {
         const int it = kb - kb_begin;
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(bar_empty(s), ph ^ 1);
-        mbar_expect_tx(bar_full(s), tx_bytes);
+        mbar_expect_tx(bar_full(s), S::TX_BYTES);
         const uint32_t sa = sbase + s * S::STAGE_BYTES;
         const uint32_t sb = sa + S::A_BYTES;
         if constexpr (CONV) {
           const int tap = kb / cblocks, cb = kb - tap * cblocks;
           const int dy = tap / p.kw, dx = tap - dy * p.kw;
           tma_load_4d(&tmX, bar_full(s), sa, cb * BLOCK_K, w0 + dx - p.pad_w, h0 + dy - p.pad_h, img);
-          tma_load_2d(&tmW, bar_full(s), sb, tap * p.C + cb * BLOCK_K, n0);
+          load_w_tile<BLOCK_N>(&tmW, bar_full(s), sb, tap * p.C + cb * BLOCK_K, kb, num_kb, n0, p.w_tiled);
           tma_load_2d(&tmD, bar_full(s), sb + BLOCK_N * 128,
                       (p.down_per_tap ? tap * p.C : 0) + cb * BLOCK_K, 0);
         } else {
           tma_load_2d(&tmX, bar_full(s), sa, kb * BLOCK_K, m0);
-          tma_load_2d(&tmW, bar_full(s), sb, kb * BLOCK_K, n0);
+          load_w_tile<BLOCK_N>(&tmW, bar_full(s), sb, kb * BLOCK_K, kb, num_kb, n0, p.w_tiled);
           tma_load_2d(&tmD, bar_full(s), sb + BLOCK_N * 128, kb * BLOCK_K, 0);
         }
       }

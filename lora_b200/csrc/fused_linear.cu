@@ -10,14 +10,12 @@
 
 namespace lb {
 
-// Single-row-tile sites (M = 77 text tokens, 64 mid-block pixels): load only the rows that exist.
-// The TMA engine, not the tensor core, paces these kernels (~2.5 clk per 128-byte box row), and rows
-// past M are pure zero fill. LB_FULL_BOX=1 restores the 128-row box (profiling).
-static int tight_rows(int M) {
-  static int off = -1;
-  if (off < 0) { const char* e = getenv("LB_FULL_BOX"); off = (e && e[0] == '1') ? 1 : 0; }
-  if (off || M > BLOCK_M - 8) return 0;
-  return (M + 7) & ~7;
+// Tensor map of the frozen weight: row-major [N, K] (box BLOCK_N x 64) or, pre-tiled by lb_tile_weight,
+// [n64 * num_kb * 64, 64] (box 64 x 64: one contiguous 8 KB block per box).
+static bool tmap_weight(CUtensorMap* tm, const void* W, CUtensorMapDataType dt, int N, int K, int block_n, int tiled) {
+  if (!tiled) return tmap_2d(tm, W, dt, 2, K, N, BLOCK_K, block_n, true);
+  const unsigned long long n64 = (N + 63) / 64, nkb = (K + BLOCK_K - 1) / BLOCK_K;
+  return tmap_2d(tm, W, dt, 2, 64, n64 * nkb * 64, 64, 64, true);
 }
 
 template <int BLOCK_N, int STAGES, typename OutT, int MIN_CTAS, bool DROP = false, bool SPLITK = false,
@@ -41,9 +39,8 @@ static int launch_linear(const void* X, const void* W, const void* Dn, void* Y, 
   const CUtensorMapDataType in_dt = p.fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
   CUtensorMap tmX, tmW, tmD, tmY;
-  p.a_rows = tight_rows(p.M);
-  if (!tmap_2d(&tmX, X, in_dt, 2, p.K, p.M, BLOCK_K, p.a_rows ? p.a_rows : BLOCK_M, true)) return LB_ERR_TMAP;
-  if (!tmap_2d(&tmW, W, in_dt, 2, p.K, p.N, BLOCK_K, BLOCK_N, true)) return LB_ERR_TMAP;
+  if (!tmap_2d(&tmX, X, in_dt, 2, p.K, p.M, BLOCK_K, BLOCK_M, true)) return LB_ERR_TMAP;
+  if (!tmap_weight(&tmW, W, in_dt, p.N, p.K, BLOCK_N, p.w_tiled)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmD, Dn, in_dt, 2, p.K, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmY, Y, out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
   dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M, SPLITK ? split : 1);
@@ -108,7 +105,7 @@ static int launch_persistent(const void* X, const void* W, const void* Dn, void*
   const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
   CUtensorMap tmX, tmW, tmD, tmY;
   if (!tmap_2d(&tmX, X, in_dt, 2, p.K, p.M, BLOCK_K, BLOCK_M, true)) return LB_ERR_TMAP;
-  if (!tmap_2d(&tmW, W, in_dt, 2, p.K, p.N, BLOCK_K, BLOCK_N, true)) return LB_ERR_TMAP;
+  if (!tmap_weight(&tmW, W, in_dt, p.N, p.K, BLOCK_N, p.w_tiled)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmD, Dn, in_dt, 2, p.K, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmY, Y, out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
   const long long total = static_cast<long long>((p.N + BLOCK_N - 1) / BLOCK_N) * ((p.M + BLOCK_M - 1) / BLOCK_M);
@@ -129,10 +126,9 @@ static int launch_grouped(GroupedArgs& a, const void* const* X, const void* cons
   const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
   int total = 0;
   for (int i = 0; i < a.n_problems; ++i) {
-    FusedParams& p = a.p[i];
-    p.a_rows = tight_rows(p.M);
-    if (!tmap_2d(&a.tmX[i], X[i], in_dt, 2, p.K, p.M, BLOCK_K, p.a_rows ? p.a_rows : BLOCK_M, true)) return LB_ERR_TMAP;
-    if (!tmap_2d(&a.tmW[i], W[i], in_dt, 2, p.K, p.N, BLOCK_K, BLOCK_N, true)) return LB_ERR_TMAP;
+    const FusedParams& p = a.p[i];
+    if (!tmap_2d(&a.tmX[i], X[i], in_dt, 2, p.K, p.M, BLOCK_K, BLOCK_M, true)) return LB_ERR_TMAP;
+    if (!tmap_weight(&a.tmW[i], W[i], in_dt, p.N, p.K, BLOCK_N, p.w_tiled)) return LB_ERR_TMAP;
     if (!tmap_2d(&a.tmD[i], Dn[i], in_dt, 2, p.K, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
     if (!tmap_2d(&a.tmY[i], Y[i], out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
     a.tile_start[i] = total;
@@ -156,7 +152,7 @@ static int launch_splitk(const void* X, const void* W, const void* Dn, void* Y, 
   const CUtensorMapDataType out_dt = out_dtype == LB_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : in_dt;
   CUtensorMap tmX, tmW, tmD, tmY;
   if (!tmap_2d(&tmX, X, in_dt, 2, p.K, p.M, BLOCK_K, BLOCK_M, true)) return LB_ERR_TMAP;
-  if (!tmap_2d(&tmW, W, in_dt, 2, p.K, p.N, BLOCK_K, BLOCK_N, true)) return LB_ERR_TMAP;
+  if (!tmap_weight(&tmW, W, in_dt, p.N, p.K, BLOCK_N, p.w_tiled)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmD, Dn, in_dt, 2, p.K, R_PAD, BLOCK_K, R_PAD, true)) return LB_ERR_TMAP;
   if (!tmap_2d(&tmY, Y, out_dt, sizeof(OutT), p.N, p.M, S::BOX_COLS, BLOCK_M, true)) return LB_ERR_TMAP;
   const dim3 grid((p.N + BLOCK_N - 1) / BLOCK_N, (p.M + BLOCK_M - 1) / BLOCK_M, SPLIT);
@@ -199,6 +195,8 @@ static int linear_fwd_impl(const void* X, const void* W, const float* bias,
                                   int in_dtype, int out_dtype, float drop_p, const void* seed_dev,
                                   void* stream, int mask_input = 0) {
   using namespace lb;
+  const int w_tiled = (in_dtype & LB_W_TILED) ? 1 : 0;
+  in_dtype &= ~LB_W_TILED;
   if (!(drop_p >= 0.f && drop_p < 1.f) || (drop_p > 0.f && (seed_dev == nullptr || T_in != nullptr)))
     return LB_ERR_SHAPE;
   if (mask_input && !(drop_p > 0.f)) return LB_ERR_SHAPE;
@@ -217,7 +215,7 @@ static int linear_fwd_impl(const void* X, const void* W, const float* bias,
   FusedParams p = {};
   p.bias = bias; p.up = up; p.up_rs = up_rs; p.up_cs = up_cs; p.up_gs = 0; p.diag = diag;
   p.t_out = T_out; p.t_in = T_in; p.scale = scale; p.M = M; p.N = N; p.K = K; p.r = r;
-  p.fmt = (in_dtype == LB_BF16) ? 1 : 0; p.t_group = 0; p.dbg = g_dbg;
+  p.fmt = (in_dtype == LB_BF16) ? 1 : 0; p.t_group = 0; p.dbg = g_dbg; p.w_tiled = w_tiled;
   p.drop_p = drop_p; p.drop_inv = 1.f / (1.f - drop_p);
   p.seed = reinterpret_cast<const unsigned long long*>(seed_dev);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -363,6 +361,8 @@ extern "C" int lb_lora_linear_fwd_grouped(int n, const void* const* X, const voi
                                           const int* M, const int* K, const int* N, const int* r,
                                           int in_dtype, int out_dtype, void* stream) {
   using namespace lb;
+  const int w_tiled = (in_dtype & LB_W_TILED) ? 1 : 0;
+  in_dtype &= ~LB_W_TILED;
   if (n < 1 || n > MAX_GROUP) return LB_ERR_SHAPE;
   if (in_dtype != LB_BF16 && in_dtype != LB_F16) return LB_ERR_DTYPE;
   if (out_dtype != in_dtype && out_dtype != LB_F32) return LB_ERR_DTYPE;
@@ -381,7 +381,7 @@ extern "C" int lb_lora_linear_fwd_grouped(int n, const void* const* X, const voi
     p.bias = bias ? bias[i] : nullptr; p.up = up[i]; p.up_rs = up_rs[i]; p.up_cs = up_cs[i]; p.up_gs = 0;
     p.diag = diag ? diag[i] : nullptr; p.t_out = T_out ? T_out[i] : nullptr; p.t_in = nullptr;
     p.scale = scale[i]; p.M = M[i]; p.N = N[i]; p.K = K[i]; p.r = r[i];
-    p.fmt = (in_dtype == LB_BF16) ? 1 : 0; p.t_group = 0; p.dbg = nullptr;
+    p.fmt = (in_dtype == LB_BF16) ? 1 : 0; p.t_group = 0; p.dbg = nullptr; p.w_tiled = w_tiled;
     a.p[i] = p;
     tiles128 += static_cast<long long>((M[i] + 127) / 128) * ((N[i] + 127) / 128);
     tiles64 += static_cast<long long>((M[i] + 127) / 128) * ((N[i] + 63) / 64);

@@ -115,7 +115,7 @@ fused_lora_persistent_kernel(const __grid_constant__ CUtensorMap tmX,
           const uint32_t sa = sbase + s * S::STAGE_BYTES;
           const uint32_t sb = sa + S::A_BYTES;
           tma_load_2d(&tmX, bar_full(s), sa, kb * BLOCK_K, m0);
-          tma_load_2d(&tmW, bar_full(s), sb, kb * BLOCK_K, n0);
+          load_w_tile<BLOCK_N>(&tmW, bar_full(s), sb, kb * BLOCK_K, kb, num_kb, n0, p.w_tiled);
           tma_load_2d(&tmD, bar_full(s), sb + BLOCK_N * 128, kb * BLOCK_K, 0);
         }
       }

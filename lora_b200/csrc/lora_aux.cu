@@ -359,6 +359,34 @@ __global__ void cast_weight_kernel(const SrcT* __restrict__ src, int src_fmt,
   }
 }
 
+// Frozen weight -> 16-bit, 64 x 64-block layout (LB_W_TILED): dst block (n64, kb) = rows
+// [(n64 * nkb + kb) * 64, +64) x 64 columns; element (n, k) of the logical [N, K] operand is read from
+// src[n * src_rs + k * src_cs] (src_rs = K, src_cs = 1: W itself; src_rs = 1, src_cs = N_out... the
+// transpose for dX), zero padded to multiples of 64. One-time preparation: simplicity over speed.
+template <typename SrcT>
+__global__ void __launch_bounds__(256)
+tile_weight_kernel(const SrcT* __restrict__ src, int src_fmt, long long src_rs, long long src_cs,
+                   uint16_t* __restrict__ dst, int N, int K, int nkb, int fmt) {
+  __shared__ float tile[64][65];
+  const int kb = blockIdx.x, n64 = blockIdx.y;
+  const bool k_fast = src_cs == 1;     // which index is contiguous in the source decides the read order
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+    const int a = i >> 6, b = i & 63;
+    const int rr = k_fast ? a : b, cc = k_fast ? b : a;       // (row in block, column in block)
+    const int n = n64 * 64 + rr, k = kb * 64 + cc;
+    float x = 0.f;
+    if (n < N && k < K) {
+      const size_t off = static_cast<size_t>(n) * src_rs + static_cast<size_t>(k) * src_cs;
+      if constexpr (sizeof(SrcT) == 4) x = src[off];
+      else x = from16(src[off], src_fmt);
+    }
+    tile[rr][cc] = x;
+  }
+  __syncthreads();
+  uint16_t* d = dst + (static_cast<size_t>(n64) * nkb + kb) * 64 * 64;
+  for (int i = threadIdx.x; i < 64 * 64; i += 256) d[i] = to16(tile[i >> 6][i & 63], fmt);
+}
+
 // fp32 -> three bf16 terms laid side by side along K ("split-bf16" operands for the fp32-faithful
 // mode): x = hi + lo + O(2^-16 |x|), hi = bf16(x), lo = bf16(x - hi).
 //   pattern 0 (activation side): [hi | lo | hi]      pattern 1 (weight side): [hi | hi | lo]
@@ -1092,6 +1120,31 @@ extern "C" int lb_cast_weight(const void* src, int src_dtype, void* dst16, void*
     cast_weight_kernel<float><<<grid, block, 0, st>>>(reinterpret_cast<const float*>(src), 0, d, dT, R, C, fmt);
   else if (src_dtype == LB_BF16 || src_dtype == LB_F16)
     cast_weight_kernel<uint16_t><<<grid, block, 0, st>>>(reinterpret_cast<const uint16_t*>(src), src_dtype == LB_BF16, d, dT, R, C, fmt);
+  else
+    return LB_ERR_DTYPE;
+  return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;
+}
+
+extern "C" long long lb_tiled_weight_elems(int N, int K) {
+  if (N <= 0 || K <= 0) return 0;
+  return static_cast<long long>((N + 63) / 64) * ((K + 63) / 64) * 64 * 64;
+}
+
+extern "C" int lb_tile_weight(const void* src, int src_dtype, long long src_rs, long long src_cs, int N, int K,
+                              void* dst16, int out_dtype, void* stream) {
+  if (N <= 0 || K <= 0) return LB_ERR_SHAPE;
+  if (out_dtype != LB_BF16 && out_dtype != LB_F16) return LB_ERR_DTYPE;
+  if (reinterpret_cast<uintptr_t>(dst16) & 15) return LB_ERR_ALIGN;
+  const int nkb = (K + 63) / 64;
+  dim3 grid(nkb, (N + 63) / 64);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint16_t* d = reinterpret_cast<uint16_t*>(dst16);
+  const int fmt = out_dtype == LB_BF16;
+  if (src_dtype == LB_F32)
+    tile_weight_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(src), 0, src_rs, src_cs, d, N, K, nkb, fmt);
+  else if (src_dtype == LB_BF16 || src_dtype == LB_F16)
+    tile_weight_kernel<uint16_t><<<grid, 256, 0, st>>>(reinterpret_cast<const uint16_t*>(src), src_dtype == LB_BF16, src_rs,
+                                                      src_cs, d, N, K, nkb, fmt);
   else
     return LB_ERR_DTYPE;
   return cudaGetLastError() == cudaSuccess ? LB_OK : LB_ERR_CUDA;

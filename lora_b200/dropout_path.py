@@ -25,7 +25,12 @@ from . import ops
 from ._C import LoraB200Error
 from .modules import _LOW, _SiteState, _compute_dtype, _fp32_master, _out_dtype
 
-_TWO_PASS = os.environ.get("LB_DROPOUT_BWD", "") == "twopass"
+# Backward formulation. "twopass" (default): lb_lora_dropout_dt (one masked pass over gY) + the plain dX
+# kernel with T_in. "fused": the mask applied inside the dX kernel (lb_lora_*_dx_dropout, one launch, no
+# extra pass). Same results (tests/test_dropout_gpu.py runs both); measured on the same box the fused
+# form is SLOWER on the extended step (26.3 vs 23.7 ms, profiles/r2g_*): hashing 8192 mask decisions per
+# K block on four warps costs more than the streaming pass it deletes.
+_TWO_PASS = os.environ.get("LB_DROPOUT_BWD", "twopass") != "fused"
 
 
 class _SeedPool:

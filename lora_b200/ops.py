@@ -128,6 +128,50 @@ def cast_weight(w: torch.Tensor, dtype, want_plain: bool, want_t: bool):
     return plain, wt
 
 
+LB_W_TILED = 0x100
+
+
+class TiledWeight:
+    """A frozen weight's 16-bit copy in the 64 x 64-block layout (include/lora_b200.h, LB_W_TILED):
+    logical operand [N, K]; accepted wherever the fused linear entries take `w16` / `wt16`."""
+    __slots__ = ("buf", "N", "K", "dtype")
+
+    def __init__(self, buf, N, K, dtype):
+        self.buf, self.N, self.K, self.dtype = buf, N, K, dtype
+
+    @property
+    def shape(self):
+        return (self.N, self.K)
+
+    def data_ptr(self):
+        return self.buf.data_ptr()
+
+
+def tile_weight(w: torch.Tensor, dtype, transpose: bool = False) -> TiledWeight:
+    """lb_tile_weight: w [R, C] (fp32/bf16/fp16, CUDA, contiguous) -> TiledWeight of w (logical [R, C]) or,
+    transpose=True, of w^T (logical [C, R]: the dX operand)."""
+    _req_cuda(w)
+    assert w.dim() == 2 and w.is_contiguous()
+    R, C = w.shape
+    N, K = (C, R) if transpose else (R, C)
+    rs, cs = (1, C) if transpose else (C, 1)
+    n = int(_C.lib.lb_tiled_weight_elems(N, K))
+    buf = torch.empty(n, device=w.device, dtype=dtype)
+    check(_C.lib.lb_tile_weight(ptr(w), dtype_code(w.dtype), rs, cs, N, K, ptr(buf), dtype_code(dtype), stream_ptr()),
+          "lb_tile_weight")
+    _count()
+    return TiledWeight(buf, N, K, dtype)
+
+
+def _w_arg(w16, K):
+    """(pointer, N, in_dtype flag) of a frozen-weight argument: row-major tensor or TiledWeight."""
+    if isinstance(w16, TiledWeight):
+        assert w16.K == K
+        return ptr(w16.buf), w16.N, LB_W_TILED
+    assert w16.shape[1] == K and w16.is_contiguous()
+    return ptr(w16), w16.shape[0], 0
+
+
 def fused_linear(x2d: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tensor],
                  down16: torch.Tensor, up: torch.Tensor, up_rs: int, up_cs: int,
                  diag: Optional[torch.Tensor], scale: float, r: int, out_dtype,
@@ -137,25 +181,25 @@ def fused_linear(x2d: torch.Tensor, w16: torch.Tensor, bias: Optional[torch.Tens
     """Y = x2d.w16^T + bias + ((x2d.down16^T) * scale*diag) . up^T ; returns (Y, T or None).
     t_in: use these rank-r activations [M,16] instead of x2d.down16^T (dropout backward).
     drop_p > 0 (+ seed: int64[1] on the device): nn.Dropout on the branch, masked in the drain."""
-    _req_cuda(x2d, w16, down16, up)
+    _req_cuda(x2d, down16, up)
     M, K = x2d.shape
-    N = w16.shape[0]
-    assert w16.shape[1] == K and down16.shape == (R_PAD, K)
-    assert x2d.is_contiguous() and w16.is_contiguous() and down16.is_contiguous()
+    wp, N, wflag = _w_arg(w16, K)
+    assert down16.shape == (R_PAD, K)
+    assert x2d.is_contiguous() and down16.is_contiguous()
     y = torch.empty((M, N), device=x2d.device, dtype=out_dtype)
     t = torch.empty((M, R_PAD), device=x2d.device, dtype=torch.float32) if want_t else None
     if drop_p > 0.0:
         assert t_in is None and seed is not None and seed.dtype == torch.int64 and seed.is_cuda
-        check(_C.lib.lb_lora_linear_fwd_dropout(ptr(x2d), ptr(w16), ptr(bias), ptr(down16), ptr(up),
+        check(_C.lib.lb_lora_linear_fwd_dropout(ptr(x2d), wp, ptr(bias), ptr(down16), ptr(up),
                                                 up_rs, up_cs, ptr(diag), float(scale), ptr(y), ptr(t),
-                                                M, K, N, r, dtype_code(x2d.dtype), dtype_code(out_dtype),
+                                                M, K, N, r, dtype_code(x2d.dtype) | wflag, dtype_code(out_dtype),
                                                 float(drop_p), ptr(seed), stream_ptr()),
               "lb_lora_linear_fwd_dropout")
         _count()
         return y, t
-    check(_C.lib.lb_lora_linear_fwd(ptr(x2d), ptr(w16), ptr(bias), ptr(down16), ptr(up),
+    check(_C.lib.lb_lora_linear_fwd(ptr(x2d), wp, ptr(bias), ptr(down16), ptr(up),
                                     up_rs, up_cs, ptr(diag), float(scale), ptr(y), ptr(t), ptr(t_in),
-                                    M, K, N, r, dtype_code(x2d.dtype), dtype_code(out_dtype),
+                                    M, K, N, r, dtype_code(x2d.dtype) | wflag, dtype_code(out_dtype),
                                     stream_ptr()), "lb_lora_linear_fwd")
     _count()
     return y, t

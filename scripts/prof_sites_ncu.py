@@ -35,6 +35,7 @@ if os.environ.get("SITES") == "small":          # the <= 148-tile sites (split-K
 if os.environ.get("SITES") == "geglu":          # the wide projections + the mid block (schedule experiments)
     SITES = [s for s in SITES if "GEGLU" in s[0] or s[0].startswith("mid")]
 TAG = os.environ.get("TAG", "")
+TILED = os.environ.get("TILED") == "1"          # frozen weight in the 64x64-block layout (LB_W_TILED)
 MODE = int(os.environ.get("MODE", 0))           # lb_debug_set_linear_mode value (0 = the planner's choice)
 
 
@@ -57,7 +58,8 @@ def run():
             d16 = ops.cast_rows_pad16(a, k, 1, r, k, dt)
             bias = torch.zeros(n, device=dev) if direction == "fwd" else None
             wt = w.t()
-            ours = lambda x=x, w=w, bias=bias, d16=d16, b=b, r=r: ops.fused_linear(x, w, bias, d16, b, r, 1, None, 1.0, r, dt, True)
+            wo = ops.tile_weight(w, dt) if TILED else w
+            ours = lambda x=x, w=wo, bias=bias, d16=d16, b=b, r=r: ops.fused_linear(x, w, bias, d16, b, r, 1, None, 1.0, r, dt, True)
             lib = lambda x=x, wt=wt: torch.matmul(x, wt)
             for _ in range(3):
                 ours(); lib()
