@@ -270,16 +270,36 @@ static int linear_fwd_impl(const void* X, const void* W, const float* bias,
     }
   }
   const int sched = g_linear_mode & 3, bn_choice = (g_linear_mode >> 2) & 3, split_choice = g_linear_mode >> 4;
-  const long long tiles128 = static_cast<long long>((M + 127) / 128) * ((N + 127) / 128);
-  // not enough 128-wide tiles to fill the SMs: halve BLOCK_N. 90-148 tiles of 128 (4096x320->320:
-  // 96) run better as ONE wave of 128-wide tiles than as 160 64-wide tiles at 3 CTAs/SM (r1c: 11.1 vs 12.3 us)
-  bool narrow = tiles128 < 90;
+  const long long m_tiles = (M + 127) / 128;
+  const long long tiles128 = m_tiles * ((N + 127) / 128);
+  const long long tiles64 = m_tiles * ((N + 63) / 64);
+  const int n_sms = sm_count();
+  if (g_linear_mode == 0 && T_in == nullptr && splitk_enabled() && n_sms > 0) {
+    // Cluster split-K (fused_splitk.cuh): few tiles and a K loop of >= 10 blocks -- the attention
+    // projections of the 16x16 / 8x8 levels, the 77-token k/v sites, CLIP. Two CTAs of a cluster halve
+    // the K loop and merge through distributed shared memory (one bulk copy, no global round trip:
+    // the L2-reduction split above costs 4-5 us and only pays for K >= 5120). Measured per site
+    // (profiles/r2g_site_table_cluster_splitk.md): 256x1280->1280 11.0 -> 9.6 us, 64x1280->1280 10.8 -> 9.0,
+    // 77x768->768 8.35 -> 7.9; K = 320 sites lose (6.7 -> 7.3) and stay unsplit.
+    if (K >= 640 && tiles64 * 2 <= n_sms) {
+      if (out_dtype == LB_F32) return launch_splitk<64, 4, float, 2>(X, W, down16, Y, p, out_dtype, st);
+      return launch_splitk<64, 6, uint16_t, 2>(X, W, down16, Y, p, out_dtype, st);
+    }
+    // One balanced wave of 192-wide tiles instead of 1.1 waves of 128-wide ones (256x1280->10240:
+    // 160 -> 108 CTAs, 18.7 -> 13.9 us)
+    if (out_dtype != LB_F32 && tiles128 > n_sms && m_tiles * ((N + 191) / 192) <= n_sms && K >= 640)
+      return launch_linear<192, 4, uint16_t, 1>(X, W, down16, Y, p, out_dtype, st);
+  }
+  // not enough tiles to fill the SMs with 128-wide ones: halve BLOCK_N -- as long as the 64-wide tiles
+  // still fit ONE wave (64x1280->10240: 80 tiles of 128 on 80 SMs take 12.9 us, 160 tiles of 64 at
+  // 3 CTAs/SM 16.6; 4096x320->320: 96 vs 160 tiles, 11.1 vs 12.3 us)
+  bool narrow = tiles64 <= n_sms;
   if (K >= 2048 && tiles128 >= 64) narrow = false;  // long K: per-tile work is large, keep W reuse
   if (bn_choice == 1) narrow = true;
   if (bn_choice == 2) narrow = false;
   // More tiles than SMs: persistent CTAs with a double-buffered TMEM accumulator (epilogue of
   // tile i overlaps the main loop of tile i+1). Otherwise one tile per CTA.
-  const long long tiles_n = narrow ? static_cast<long long>((M + 127) / 128) * ((N + 63) / 64) : tiles128;
+  const long long tiles_n = narrow ? tiles64 : tiles128;
   if (sched == 3 && T_in == nullptr) {
     // EXPERIMENTAL, opt-in only: split the K loop of every tile across a cluster of 2..4 CTAs
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
