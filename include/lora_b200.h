@@ -38,8 +38,8 @@ enum lb_dtype { LB_BF16 = 0, LB_F16 = 1, LB_F32 = 2 };
  * entry) is NOT row-major [N, K] but the 64 x 64-block layout written by lb_tile_weight -- block
  * (n64, kb) occupies rows [(n64 * ceil(K/64) + kb) * 64, +64) of a [rows, 64] 16-bit tensor, zero padded
  * -- so that every TMA box of the weight stream is one contiguous 8 KB run of HBM (a row-major box is
- * 64-192 rows of 128 bytes a whole K apart: one DRAM page activation per 128-256 bytes). The frozen
- * weights are the cold, never-rewritten bulk of a step's traffic; their 16-bit copy is ours to lay out. */
+ * 64-192 rows of 128 bytes a whole K apart). Optional: measured on B200 against row-major on every
+ * SD1.5 site shape it is neither faster nor slower (profiles/r2h_site_table_tiled_vs_rowmajor.md). */
 #define LB_W_TILED 0x100
 
 /* ABI version of this header (bumped on any signature change). */

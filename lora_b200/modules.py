@@ -135,23 +135,35 @@ class _SiteState:
     def __deepcopy__(self, memo):
         return _SiteState()
 
-    def frozen(self, weight2d: torch.Tensor, dtype, need_t: bool):
+    def frozen(self, weight2d: torch.Tensor, dtype, need_t: bool, tiled: Optional[bool] = None):
+        """16-bit copies of the frozen weight: (W [N,K], W^T [K,N] or None), row-major tensors -- or, with
+        ops.TILED_WEIGHTS (opt-in, LB_TILED_W=1; measured: no gain), ops.TiledWeight in contiguous
+        64 x 64 blocks. tiled=False forces row-major (row slicing: the rank > 16 chunks)."""
+        tiled = ops.TILED_WEIGHTS if tiled is None else tiled
         k = _key(weight2d)
-        ent = self.w.get(dtype)
+        slot = (dtype, "tiled") if tiled else dtype
+        ent = self.w.get(slot)
         if ent is not None and ent[0] != k:
             ent = None
         have_plain = ent is not None
         have_t = ent is not None and ent[2] is not None
         if not have_plain or (need_t and not have_t):
-            reuse = weight2d.dtype == dtype and weight2d.is_contiguous()
-            make_plain = not have_plain and not reuse
-            w16, wt16 = ops.cast_weight(weight2d, dtype, make_plain, need_t)
-            if have_plain:
-                w16 = ent[1]
-            elif reuse:
-                w16 = weight2d.detach()
+            if tiled:
+                src = weight2d.detach()
+                if not src.is_contiguous():
+                    src = src.contiguous()
+                w16 = ent[1] if have_plain else ops.tile_weight(src, dtype)
+                wt16 = ops.tile_weight(src, dtype, transpose=True) if need_t else None
+            else:
+                reuse = weight2d.dtype == dtype and weight2d.is_contiguous()
+                make_plain = not have_plain and not reuse
+                w16, wt16 = ops.cast_weight(weight2d, dtype, make_plain, need_t)
+                if have_plain:
+                    w16 = ent[1]
+                elif reuse:
+                    w16 = weight2d.detach()
             ent = (k, w16, wt16 if need_t else None)
-            self.w[dtype] = ent
+            self.w[slot] = ent
         return ent[1], ent[2]
 
     def bias32(self, bias: Optional[torch.Tensor]):

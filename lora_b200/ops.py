@@ -5,6 +5,8 @@ LoRA path happens in liblora_b200.so. There is deliberately no eager fallback in
 """
 from typing import Optional, Tuple
 
+import os
+
 import torch
 
 from . import _C
@@ -129,7 +131,11 @@ def cast_weight(w: torch.Tensor, dtype, want_plain: bool, want_t: bool):
 
 
 LB_W_TILED = 0x100
-
+# LB_TILED_W=1: the module layer (modules._SiteState.frozen) keeps its frozen-weight copies in the
+# 64x64-block layout. OFF by default: measured per site against row-major on the same box
+# (profiles/r2h_site_table_tiled_vs_rowmajor.md) it changes nothing -- DRAM page locality of the weight
+# stream is not what limits these kernels -- and it costs a second copy of every 16-bit frozen weight.
+TILED_WEIGHTS = os.environ.get("LB_TILED_W", "0") == "1"
 
 class TiledWeight:
     """A frozen weight's 16-bit copy in the 64 x 64-block layout (include/lora_b200.h, LB_W_TILED):
@@ -313,15 +319,15 @@ def wgrad_shift(S_rows: torch.Tensor, V: torch.Tensor, diag, scale: float, out: 
 def fused_linear_dx_dropout(gy2d: torch.Tensor, wt16: torch.Tensor, upT16: torch.Tensor, A32: torch.Tensor,
                             diag, scale: float, r: int, out_dtype, p: float, seed: torch.Tensor):
     """dX = gY.W + (((mask o gY).B) * scale*diag/(1-p)) . A  and  dTm = (mask o gY).B  (one launch)."""
-    _req_cuda(gy2d, wt16, upT16, A32, seed)
+    _req_cuda(gy2d, upT16, A32, seed)
     M, N_out = gy2d.shape
-    K_in = wt16.shape[0]
-    assert wt16.shape[1] == N_out and upT16.shape == (R_PAD, N_out) and gy2d.is_contiguous()
+    wp, K_in, wflag = _w_arg(wt16, N_out)
+    assert upT16.shape == (R_PAD, N_out) and gy2d.is_contiguous()
     dX = torch.empty((M, K_in), device=gy2d.device, dtype=out_dtype)
     dTm = torch.empty((M, R_PAD), device=gy2d.device, dtype=torch.float32)
-    check(_C.lib.lb_lora_linear_dx_dropout(ptr(gy2d), ptr(wt16), ptr(upT16), ptr(A32), 1, K_in, ptr(diag),
+    check(_C.lib.lb_lora_linear_dx_dropout(ptr(gy2d), wp, ptr(upT16), ptr(A32), 1, K_in, ptr(diag),
                                            float(scale), ptr(dX), ptr(dTm), M, N_out, K_in, r,
-                                           dtype_code(gy2d.dtype), dtype_code(out_dtype), float(p), ptr(seed),
+                                           dtype_code(gy2d.dtype) | wflag, dtype_code(out_dtype), float(p), ptr(seed),
                                            stream_ptr()), "lb_lora_linear_dx_dropout")
     _count()
     return dX, dTm
@@ -429,9 +435,11 @@ def fused_linear_grouped(problems, out_dtype, want_t: bool):
     assert 1 <= n <= 4
     VP, LL, I, F = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_float
     ys, ts = [], []
+    tiled = isinstance(problems[0][1], TiledWeight)
     for (x, w, b, d, up, rs, cs, diag, sc, r) in problems:
-        _req_cuda(x, w, d, up)
-        assert x.is_contiguous() and w.is_contiguous() and d.is_contiguous() and w.shape[1] == x.shape[1]
+        _req_cuda(x, d, up)
+        assert isinstance(w, TiledWeight) == tiled, "a grouped launch takes one weight layout"
+        assert x.is_contiguous() and (tiled or w.is_contiguous()) and d.is_contiguous() and w.shape[1] == x.shape[1]
         ys.append(torch.empty((x.shape[0], w.shape[0]), device=x.device, dtype=out_dtype))
         ts.append(torch.empty((x.shape[0], R_PAD), device=x.device, dtype=torch.float32) if want_t else None)
     dp = lambda t: None if t is None else t.data_ptr()
@@ -452,8 +460,8 @@ def fused_linear_grouped(problems, out_dtype, want_t: bool):
     N = arr(I, [p[1].shape[0] for p in problems])
     R = arr(I, [p[9] for p in problems])
     check(_C.lib.lb_lora_linear_fwd_grouped(n, X, W, B, D, U, RS, CS, DG, SC, Y, T, M, K, N, R,
-                                            dtype_code(problems[0][0].dtype), dtype_code(out_dtype),
-                                            stream_ptr()), "lb_lora_linear_fwd_grouped")
+                                            dtype_code(problems[0][0].dtype) | (LB_W_TILED if tiled else 0),
+                                            dtype_code(out_dtype), stream_ptr()), "lb_lora_linear_fwd_grouped")
     _count()
     return ys, ts
 

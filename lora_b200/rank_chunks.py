@@ -39,7 +39,7 @@ class _ChunkedLoraLinearFn(torch.autograd.Function):
         x2d = x.reshape(-1, K)
         if x2d.dtype != cdt or not x2d.is_contiguous():
             x2d = x2d.to(cdt).contiguous()
-        w16, _ = st.frozen(lin.weight, cdt, need_t=False)
+        w16, _ = st.frozen(lin.weight, cdt, need_t=False, tiled=False)
         b32 = st.bias32(lin.bias)
         A32, B32 = _fp32_master(A), _fp32_master(B)
         diag = mod._selector_diag()
@@ -72,7 +72,7 @@ class _ChunkedLoraLinearFn(torch.autograd.Function):
         gy2d = gy.reshape(-1, N)
         if gy2d.dtype != cdt or not gy2d.is_contiguous():
             gy2d = gy2d.to(cdt).contiguous()
-        _, wt16 = st.frozen(lin.weight, cdt, need_t=True)
+        _, wt16 = st.frozen(lin.weight, cdt, need_t=True, tiled=False)
         A32, B32 = _fp32_master(A), _fp32_master(B)
         dx_dtype = ctx.x_dtype if ctx.x_dtype in _LOW else torch.float32
         need_x, need_a, need_b = ctx.needs_input_grad[:3]
