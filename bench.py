@@ -80,7 +80,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -91,13 +91,26 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def wait_ready(self, timeout=3.0):
+        """nvidia-smi needs a few hundred ms before its first sample: block until it is producing."""
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        """Start of the timed region (the GPU is idle and the host is about to enqueue it)."""
+        self.i0 = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        i1 = len(self.lines)                       # host has synchronised: the timed region is over
+        time.sleep(0.08)
         self.proc.terminate()
+        i0 = getattr(self, "i0", 0)
+        window = self.lines[i0:max(i1, i0 + 1)] or self.lines[-1:]
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -414,10 +427,13 @@ def run_native(args):
     # ---------------- device-resident timing (value)
     for _ in range(max(args.warmup, 3)):
         trainer.step_device()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
+    barrier()
+    if rank == 0:
+        sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
