@@ -50,37 +50,64 @@ class _WgProblemC(_ct.Structure):
 
 
 _WG_QUEUE = None      # None: launch immediately; dict dtype -> [(_WgProblemC fields, keepalive)]
+_WG_SIDE = None       # deferral with overlap: full batches of 24 leave on this stream as soon as they fill
+WG_BATCH = 24
 
 
-def wgrad_defer_begin():
-    global _WG_QUEUE
+def wgrad_defer_begin(side_stream=None):
+    """side_stream: launch every full batch of 24 queued reductions on it right away (after everything
+    enqueued so far on the current stream), so the batches overlap the rest of the backward pass instead
+    of trailing it; the caller joins the stream after wgrad_flush()."""
+    global _WG_QUEUE, _WG_SIDE
     _WG_QUEUE = {}
+    _WG_SIDE = side_stream
 
 
 def wgrad_defer_cancel():
-    global _WG_QUEUE
+    global _WG_QUEUE, _WG_SIDE
     _WG_QUEUE = None
+    _WG_SIDE = None
+
+
+def _wgrad_launch(dtype, items, side):
+    arr = (_WgProblemC * len(items))(*[_WgProblemC(*it[0]) for it in items])
+    if side is None:
+        check(_C.lib.lb_lora_wgrad_batch(arr, len(items), dtype_code(dtype), stream_ptr()), "lb_lora_wgrad_batch")
+    else:
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            check(_C.lib.lb_lora_wgrad_batch(arr, len(items), dtype_code(dtype), stream_ptr()), "lb_lora_wgrad_batch")
+        for it in items:                   # the operands must outlive the side-stream launch
+            for t in it[1]:
+                if t is not None:
+                    t.record_stream(side)
+    n = (len(items) + WG_BATCH - 1) // WG_BATCH
+    _count(n)
+    return n
 
 
 def _wgrad_enqueue(S, V, out, out_js, out_cs, M, C, r, scale, diag, drop_p=0.0, seed=None, conv=None):
     dp = lambda t: None if t is None else t.data_ptr()
     item = (dp(S), dp(V), dp(out), int(out_js), int(out_cs), int(M), int(C), int(r), float(scale), dp(diag),
             float(drop_p), dp(seed)) + (tuple(int(v) for v in conv) if conv is not None else (0, 0, 0, 0, 0, 0))
-    _WG_QUEUE.setdefault(S.dtype, []).append((item, (S, V, out, diag, seed)))
+    lst = _WG_QUEUE.setdefault(S.dtype, [])
+    lst.append((item, (S, V, out, diag, seed)))
+    if _WG_SIDE is not None and len(lst) >= WG_BATCH:
+        _wgrad_launch(S.dtype, lst[:WG_BATCH], _WG_SIDE)
+        del lst[:WG_BATCH]
 
 
 def wgrad_flush():
     """Run every queued reduction (lb_lora_wgrad_batch) and leave deferral mode."""
-    global _WG_QUEUE
+    global _WG_QUEUE, _WG_SIDE
     q, _WG_QUEUE = _WG_QUEUE, None
+    side, _WG_SIDE = _WG_SIDE, None
     if not q:
         return 0
     n_launch = 0
     for dtype, items in q.items():
-        arr = (_WgProblemC * len(items))(*[_WgProblemC(*it[0]) for it in items])
-        check(_C.lib.lb_lora_wgrad_batch(arr, len(items), dtype_code(dtype), stream_ptr()), "lb_lora_wgrad_batch")
-        n_launch += (len(items) + 23) // 24
-    _count(n_launch)
+        if items:
+            n_launch += _wgrad_launch(dtype, items, side)
     return n_launch
 
 

@@ -216,8 +216,11 @@ class LoraTrainStep:
         import os as _os
         defer = (cfg.defer_wgrad and self._side is None and lat.is_cuda and hasattr(self, "arena")
                  and _os.environ.get("LB_NO_DEFER", "0") != "1")
+        overlap = defer and _os.environ.get("LB_WGRAD_OVERLAP", "0") == "1"
+        if overlap and getattr(self, "_wg_side", None) is None:
+            self._wg_side = torch.cuda.Stream(device=self.device)
         if defer:
-            ops.wgrad_defer_begin()
+            ops.wgrad_defer_begin(self._wg_side if overlap else None)
         try:
             loss.backward()
             if defer:
@@ -225,6 +228,8 @@ class LoraTrainStep:
         finally:
             ops.set_side_stream(None)
             ops.wgrad_defer_cancel()
+        if overlap:
+            torch.cuda.current_stream().wait_stream(self._wg_side)   # join: every batch has landed in arena.g
         if self._side is not None:
             torch.cuda.current_stream().wait_stream(self._side)   # join: all dA/dB are in arena.g
         dropout_path.end_step()
