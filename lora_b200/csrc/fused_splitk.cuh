@@ -1,6 +1,7 @@
-// EXPERIMENTAL (opt-in through lb_debug_set_linear_mode, never chosen automatically; written after
-// round 1's GPU budget was spent, so it has been compiled and inspected but NOT yet run):
-// cluster split-K variant of the fused LoRA linear kernel for the small-M / long-K sites.
+// Cluster split-K variant of the fused LoRA linear kernel for the few-tile sites (written at the end of
+// round 1, first run in round 2; since visit 8 the planner's choice for K >= 640 sites whose 64-wide
+// tiles fill at most half the SMs -- lb_lora_linear_fwd in fused_linear.cu; lb_debug_set_linear_mode
+// schedule 3 forces it with 2..4 CTAs). Measured: profiles/r2g_site_table_cluster_splitk.md.
 //
 // Why: a CTA pulls operands at ~50 B/clk however many CTAs are running (per-SM L2->SMEM port), so a
 // 77x768->768 or 256x1280->1280 site -- 12...40 tiles -- streams its whole K loop on a handful of
