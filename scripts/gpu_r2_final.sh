@@ -1,0 +1,28 @@
+#!/bin/bash
+# Round-2 final visit (1 GPU), as the driver runs things on a fresh box: whole GPU suite, smoke(), default
+# bench and its reference arm; then the evidence passes for profiles/: DRAM traffic of the sweep, ncu
+# --set full of every hand-written kernel.
+mkdir -p gpurun_out
+L=gpurun_out/final2.log
+echo "build $(cut -c1-12 lora_b200/.liblora_b200.stamp)" > $L
+echo "=== pytest -m gpu (all)" >> $L
+timeout 1500 python -m pytest tests -x -q -m gpu --timeout 600 -p no:cacheprovider 2>&1 | tail -6 >> $L
+echo "=== smoke()" >> $L
+timeout 900 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | cut -c1-200 >> $L
+echo "=== bench default" >> $L
+timeout 1200 python bench.py > gpurun_out/final2_bench.json 2>> $L
+cut -c1-400 gpurun_out/final2_bench.json >> $L
+echo "=== bench --impl reference (CPU port, bounded)" >> $L
+timeout 1500 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final2_bench_ref.json 2>> $L
+cut -c1-600 gpurun_out/final2_bench_ref.json >> $L
+echo "=== DRAM traffic of the sweep" >> $L
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'fused_lora' --csv \
+   --log-file gpurun_out/final2_traffic.csv python bench.py --roofline-only > /dev/null 2>> $L
+python scripts/summarize_traffic.py gpurun_out/final2_traffic.csv 240 >> $L 2>&1
+cp profiles/fused_linear_dram_traffic.json gpurun_out/fused_linear_dram_traffic.json
+echo "=== ncu --set full, every kernel" >> $L
+timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -f \
+   -o gpurun_out/r2_kernels_final python scripts/prof_kernels_full.py >> $L 2>&1
+ls -la gpurun_out/r2_kernels_final.ncu-rep >> $L 2>&1
+ncu -i gpurun_out/r2_kernels_final.ncu-rep --page raw --csv 2>/dev/null | python scripts/summarize_ncu_full.py > gpurun_out/r2_ncu_per_kernel_final.md 2>> $L
+grep -v "Warning\|Consider\|^$\|importlib\|swigvar\|-- Docs" $L | tail -40 | cut -c1-600

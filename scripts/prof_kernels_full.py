@@ -30,7 +30,8 @@ def lin_case(M, K, N, r=4):
 
 cases = []
 # fused linear: persistent (GEGLU fwd), one tile per CTA, split-K (GEGLU dX), grouped q/k/v
-for shape in ((4096, 320, 2560), (1024, 640, 640), (256, 10240, 1280)):
+# + the cluster split-K kernel (256x1280->1280) and the 192-wide single-wave tile (256x1280->10240)
+for shape in ((4096, 320, 2560), (1024, 640, 640), (256, 10240, 1280), (256, 1280, 1280), (256, 1280, 10240)):
     x, w, bias, d16, b, r = lin_case(*shape)
     cases.append(lambda x=x, w=w, bias=bias, d16=d16, b=b, r=r: ops.fused_linear(x, w, bias, d16, b, r, 1, None, 1.0, r, dt, True))
 xq = torch.randn(1024, 640, device=dev, dtype=dt)
