@@ -3,6 +3,7 @@
 // frozen weights, the input gradient. Replaces LoraInjectedConv2d.forward
 // (/root/reference/lora_diffusion/lora.py:130-135) and the dX part of its autograd backward.
 // Kernel: fused_core.cuh.
+#include <stdlib.h>
 #include "fused_core.cuh"
 #include "lora_b200.h"
 #include "tmap.h"
@@ -106,7 +107,13 @@ static int conv2d_fwd_impl(const void* X, const void* W, const float* bias,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
 
   const long long tiles128 = static_cast<long long>(n_img) * p.tiles_h * p.tiles_w * ((Cout + 127) / 128);
-  const bool narrow = tiles128 < 120;
+  // 64-wide tiles only while they still fit ONE wave (one CTA per SM: two of these rings do not fit an SM):
+  // the 64x64-pixel, Cout = 320 sites are 96 tiles of 128 but 160 of 64 -- a second wave over 45-135 K
+  // blocks (LB_CONV_NARROW_OLD=1 restores the round-2a rule `tiles128 < 120` for A/B)
+  static int old_rule = -1;
+  if (old_rule < 0) { const char* e = getenv("LB_CONV_NARROW_OLD"); old_rule = (e && e[0] == '1') ? 1 : 0; }
+  const long long tiles64c = static_cast<long long>(n_img) * p.tiles_h * p.tiles_w * ((Cout + 63) / 64);
+  const bool narrow = old_rule ? tiles128 < 120 : tiles64c <= sm_count();
 #define LB_CONV(BN, OT, GG) launch_conv<BN, 4, OT, GG>(X, W, down16, Y, p, n_img, down_cols, out_dtype, st)
   const int cblocks = (Cin + BLOCK_K - 1) / BLOCK_K;
   const ConvPlan sp = plan_conv_split(static_cast<long long>(n_img) * p.tiles_h * p.tiles_w, taps * cblocks, Cout,
