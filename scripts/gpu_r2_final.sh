@@ -15,6 +15,15 @@ cut -c1-400 gpurun_out/final2_bench.json >> $L
 echo "=== bench --impl reference (CPU port, bounded)" >> $L
 timeout 1500 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final2_bench_ref.json 2>> $L
 cut -c1-600 gpurun_out/final2_bench_ref.json >> $L
+for old in 1 0; do
+  echo "=== bench extended, LB_CONV_NARROW_OLD=$old (conv planner A/B, same box)" >> $L
+  LB_CONV_NARROW_OLD=$old timeout 900 python bench.py --extended --rank 8 --steps 30 --warmup 5 --no-cpu-baseline --no-cuda-baseline > gpurun_out/final2_bench_ext_old$old.json 2>> $L
+  python - >> $L <<PY
+import json
+d = json.load(open("gpurun_out/final2_bench_ext_old$old.json"))
+print("images/s %.2f  ms/step %.3f  conv sweep ms %.3f (frac %.4f)  linear sweep ms %.3f" % (d["value"], d["ms_per_step"], d["roofline_conv"]["ms_per_sweep"], d["roofline_conv"]["frac"], d["roofline"]["ms_per_sweep"]))
+PY
+done
 echo "=== DRAM traffic of the sweep" >> $L
 timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:'fused_lora' --csv \
    --log-file gpurun_out/final2_traffic.csv python bench.py --roofline-only > /dev/null 2>> $L
