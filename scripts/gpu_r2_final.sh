@@ -13,8 +13,8 @@ echo "=== bench default" >> $L
 timeout 1200 python bench.py > gpurun_out/final2_bench.json 2>> $L
 cut -c1-400 gpurun_out/final2_bench.json >> $L
 echo "=== bench --impl reference (CPU port, bounded)" >> $L
-timeout 1500 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final2_bench_ref.json 2>> $L
-cut -c1-600 gpurun_out/final2_bench_ref.json >> $L
+timeout 600 python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/final2_bench_ref.json 2>> $L
+cut -c1-400 gpurun_out/final2_bench_ref.json >> $L
 for old in 1 0; do
   echo "=== bench extended, LB_CONV_NARROW_OLD=$old (conv planner A/B, same box)" >> $L
   LB_CONV_NARROW_OLD=$old timeout 900 python bench.py --extended --rank 8 --steps 30 --warmup 5 --no-cpu-baseline --no-cuda-baseline > gpurun_out/final2_bench_ext_old$old.json 2>> $L
@@ -31,7 +31,11 @@ python scripts/summarize_traffic.py gpurun_out/final2_traffic.csv 240 >> $L 2>&1
 cp profiles/fused_linear_dram_traffic.json gpurun_out/fused_linear_dram_traffic.json
 echo "=== ncu --set full, every kernel" >> $L
 timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off -f \
-   -o gpurun_out/r2_kernels_final python scripts/prof_kernels_full.py >> $L 2>&1
-ls -la gpurun_out/r2_kernels_final.ncu-rep >> $L 2>&1
-ncu -i gpurun_out/r2_kernels_final.ncu-rep --page raw --csv 2>/dev/null | python scripts/summarize_ncu_full.py > gpurun_out/r2_ncu_per_kernel_final.md 2>> $L
+   -o /tmp/r2_kernels_final python scripts/prof_kernels_full.py > /dev/null 2>&1
+ls -la /tmp/r2_kernels_final.ncu-rep >> $L 2>&1
+# the report itself is ~70 MB (gpurun_out/ is capped at 64 MiB): keep the summary and the raw CSV page
+ncu -i /tmp/r2_kernels_final.ncu-rep --page raw --csv 2>/dev/null > /tmp/r2_raw.csv
+python scripts/summarize_ncu_full.py < /tmp/r2_raw.csv > gpurun_out/r2_ncu_per_kernel_final.md 2>> $L
+gzip -c /tmp/r2_raw.csv > gpurun_out/r2_ncu_raw_final.csv.gz
+ls -la gpurun_out >> $L 2>&1
 grep -v "Warning\|Consider\|^$\|importlib\|swigvar\|-- Docs" $L | tail -40 | cut -c1-600
