@@ -47,6 +47,15 @@ def test_argument_validation_without_gpu():
     assert L.lb_lora_wgrad(p, p, None, 1.0, p, 1, 1, 8, 60, 4, 0, None) == -1
     assert L.lb_lora_wgrad(p, p, None, 1.0, p, 1, 1, 8, 64, 0, 0, None) == -2
     assert L.lb_cast_rows_pad16(p, 1, 1, p, 4, 64, 2, None) == -3
+    # frozen-weight block layout: host-side size query and refusals of the tiler
+    assert L.lb_tiled_weight_elems(320, 768) == 5 * 12 * 64 * 64
+    assert L.lb_tiled_weight_elems(1000, 136) == 16 * 3 * 64 * 64
+    assert L.lb_tiled_weight_elems(0, 64) == 0
+    assert L.lb_tile_weight(p, 0, 64, 1, 0, 64, p, 0, None) == -1          # N = 0
+    assert L.lb_tile_weight(p, 0, 64, 1, 64, 64, p, 2, None) == -3         # fp32 is not a 16-bit operand type
+    assert L.lb_tile_weight(p, 0, 64, 1, 64, 64, ctypes.c_void_p(base + 2), 0, None) == -4
+    # the LB_W_TILED flag does not hide a bad dtype
+    assert L.lb_lora_linear_fwd(p, p, None, p, p, 4, 1, None, 1.0, p, None, None, 8, 64, 64, 4, 0x100 | 2, 0, None) == -3
 
 
 def test_missing_library_fails_loudly(tmp_path, monkeypatch):
