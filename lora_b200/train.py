@@ -145,6 +145,7 @@ class LoraTrainStep:
         self.unet.train()
         self.text_encoder.train()
         self._side = torch.cuda.Stream(device=self.device) if cfg.async_wgrad else None
+        self._wg_side = None       # LB_WGRAD_OVERLAP=1: stream of the overlapped dA/dB batches (created on first use)
 
     # ------------------------------------------------------------------ the step body
     def _fwd_bwd(self):
@@ -414,6 +415,7 @@ class TextualInversionStep(LoraTrainStep):
             self.inpaint_mask = torch.zeros((latent_shape[0], 1, latent_shape[2], latent_shape[3]), device=self.device)
             self.masked_latents = torch.zeros(latent_shape, device=self.device, dtype=torch.float32)
         self._side = None
+        self._wg_side = None
         self._world = 1
         self.global_step = 0
         self.graph = self.graph_update = None
